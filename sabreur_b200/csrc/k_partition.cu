@@ -1,0 +1,179 @@
+// k_partition.cu -- kernel 3: stable per-barcode histogram + exclusive scan + scatter.
+//
+// Replaces the implicit partition of the reference: every record is appended, in input order, to
+// the file of the barcode it matched or to the unknown file (src/demux.rs:58-59, 62-63, 104-108,
+// 117-121) and counted in nb_records (src/demux.rs:58, 104, 117).  Here the same partition is
+// returned as index lists: order[bin_start[b] .. bin_start[b+1]) = the records of bin b in input
+// order, bin_count[b] = how many.  Bin n_barcodes is "unknown".
+//
+// A stable counting sort over <= 65535 bins:
+//   k_hist    every warp owns a contiguous slice of the records and counts its bins in shared memory
+//             -> cnt[bin][slice]                                    (reads assign once, 2 B/record)
+//   k_binscan one block per bin: exclusive scan of cnt[bin][*] in place, bin totals -> bin_count
+//   k_binstart single block: exclusive scan of bin_count -> bin_start
+//   k_scatter same slices; per warp a running cursor per bin in shared memory; __match_any_sync
+//             ranks equal bins inside each 32-record step so ties keep input order
+//                                                                   (reads assign again, writes 4 B/record)
+#include "sbr_common.cuh"
+
+namespace sbr {
+
+namespace {
+
+constexpr int PART_THREADS = 256;
+constexpr int PART_WARPS = PART_THREADS / 32;
+
+// records [slice_lo, slice_hi) of warp-slice v out of V: equal contiguous chunks, multiple of 32
+__device__ __forceinline__ void slice_range(uint32_t n, uint32_t V, uint32_t v, uint32_t& lo, uint32_t& hi) {
+    uint32_t per = (n + V - 1) / V;
+    per = (per + 31u) & ~31u;
+    uint64_t a = (uint64_t)per * v, b = a + per;
+    lo = a < n ? (uint32_t)a : n;
+    hi = b < n ? (uint32_t)b : n;
+}
+
+__global__ void __launch_bounds__(PART_THREADS) k_hist(const uint16_t* __restrict__ assign,
+                                                       const BatchHeader* __restrict__ hdr, uint32_t nbins,
+                                                       uint32_t* __restrict__ cnt /* [nbins][V] */) {
+    extern __shared__ uint32_t s_cnt[];  // [PART_WARPS][nbins]
+    const uint32_t n = hdr->n_records;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t V = gridDim.x * PART_WARPS, v = blockIdx.x * PART_WARPS + warp;
+    uint32_t* mine = s_cnt + (size_t)warp * nbins;
+    for (uint32_t b = lane; b < nbins; b += 32) mine[b] = 0;
+    __syncwarp();
+    uint32_t lo, hi;
+    slice_range(n, V, v, lo, hi);
+    for (uint32_t i = lo + lane; i < hi; i += 32) atomicAdd(&mine[assign[i]], 1u);
+    __syncwarp();
+    for (uint32_t b = lane; b < nbins; b += 32) cnt[(size_t)b * V + v] = mine[b];
+}
+
+// one block per bin: in-place exclusive scan over the V slices of that bin
+__global__ void __launch_bounds__(PART_THREADS) k_binscan(uint32_t* __restrict__ cnt, uint32_t V,
+                                                          uint32_t* __restrict__ bin_count) {
+    __shared__ uint32_t s_warp[PART_WARPS];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* row = cnt + (size_t)blockIdx.x * V;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < V; base += PART_THREADS) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t x = i < V ? row[i] : 0u;
+        uint32_t inc = warp_incl_scan(x, lane);
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t pre = s_carry, tot = 0;
+#pragma unroll
+        for (int w = 0; w < PART_WARPS; ++w) {
+            uint32_t t = s_warp[w];
+            if (w < warp) pre += t;
+            tot += t;
+        }
+        if (i < V) row[i] = pre + inc - x;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bin_count[blockIdx.x] = s_carry;
+}
+
+__global__ void __launch_bounds__(1024) k_binstart(const uint32_t* __restrict__ bin_count, uint32_t nbins,
+                                                   uint32_t* __restrict__ bin_start /* nbins+1 */) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nbins; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t x = i < nbins ? bin_count[i] : 0u;
+        uint32_t inc = warp_incl_scan(x, lane);
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t pre = s_carry, tot = 0;
+        for (int w = 0; w < 32; ++w) {
+            uint32_t t = s_warp[w];
+            if (w < warp) pre += t;
+            tot += t;
+        }
+        if (i < nbins) bin_start[i] = pre + inc - x;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bin_start[nbins] = s_carry;
+}
+
+__global__ void __launch_bounds__(PART_THREADS) k_scatter(const uint16_t* __restrict__ assign,
+                                                          const BatchHeader* __restrict__ hdr, uint32_t nbins,
+                                                          const uint32_t* __restrict__ cnt /* scanned */,
+                                                          const uint32_t* __restrict__ bin_start,
+                                                          uint32_t* __restrict__ order) {
+    extern __shared__ uint32_t s_cur[];  // [PART_WARPS][nbins] running cursor per bin
+    const uint32_t n = hdr->n_records;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t V = gridDim.x * PART_WARPS, v = blockIdx.x * PART_WARPS + warp;
+    uint32_t* cur = s_cur + (size_t)warp * nbins;
+    uint32_t lo, hi;
+    slice_range(n, V, v, lo, hi);
+    if (lo >= hi) return;  // warp-uniform
+    for (uint32_t b = lane; b < nbins; b += 32) cur[b] = bin_start[b] + cnt[(size_t)b * V + v];
+    __syncwarp();
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t i0 = lo; i0 < hi; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool live = i < hi;
+        const uint32_t bin = live ? assign[i] : 0xFFFFFFFFu;  // dead lanes form their own group
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, bin);
+        const uint32_t rank = __popc(peers & lt);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (live && lane == leader) {
+            base = cur[bin];
+            cur[bin] = base + __popc(peers);
+        }
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (live) order[base + rank] = i;
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+struct PartitionPlan {
+    int grid;      // blocks of k_hist / k_scatter
+    uint32_t V;    // warp slices
+    size_t smem;   // dynamic shared bytes
+};
+
+PartitionPlan partition_plan(uint32_t nbins, uint32_t max_records, int sms) {
+    PartitionPlan p;
+    size_t smem = (size_t)PART_WARPS * nbins * sizeof(uint32_t);
+    size_t fit = (200 * 1024) / (smem ? smem : 1);
+    int per_sm = fit < 1 ? 1 : (fit > 4 ? 4 : (int)fit);
+    uint32_t want = (max_records + PART_THREADS * 8 - 1) / (PART_THREADS * 8);  // >= 8 steps per warp
+    p.grid = (int)max(1u, min(want, (uint32_t)(sms * per_sm)));
+    p.V = (uint32_t)p.grid * PART_WARPS;
+    p.smem = smem;
+    return p;
+}
+
+cudaError_t partition_prepare() {
+    cudaError_t e = cudaFuncSetAttribute(k_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+}
+
+cudaError_t partition_launch(const uint16_t* d_assign, const BatchHeader* d_hdr, uint32_t nbins, uint32_t* d_cnt,
+                             uint32_t* d_bin_count, uint32_t* d_bin_start, uint32_t* d_order, const PartitionPlan& p,
+                             cudaStream_t stream) {
+    k_hist<<<p.grid, PART_THREADS, p.smem, stream>>>(d_assign, d_hdr, nbins, d_cnt);
+    k_binscan<<<nbins, PART_THREADS, 0, stream>>>(d_cnt, p.V, d_bin_count);
+    k_binstart<<<1, 1024, 0, stream>>>(d_bin_count, nbins, d_bin_start);
+    k_scatter<<<p.grid, PART_THREADS, p.smem, stream>>>(d_assign, d_hdr, nbins, d_cnt, d_bin_start, d_order);
+    return cudaGetLastError();
+}
+
+}  // namespace sbr

@@ -1,0 +1,286 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+Bit-exact: assignments, record offsets, per-bin counts, per-bin index lists, per-bin output bytes.
+Run on the B200 box: python -m pytest tests -m gpu"""
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+from conftest import fixture_bytes, read_barcode_table
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("gpu-marked test without a CUDA device (there is no CPU fallback to test)")
+    from sabreur_b200 import _ffi, demux, synth
+    _ffi.load()
+    return dict(torch=torch, ffi=_ffi, demux=demux, synth=synth)
+
+
+def _bcs(name):
+    return [r[0].encode() for r in read_barcode_table(name)]
+
+
+def _check_against_oracle(gpu, text: bytes, barcodes, m, **kw):
+    """stream `text` through the GPU and compare everything with the oracle"""
+    dm = gpu["demux"]
+    got = dm.demux_bytes(text, barcodes, m, **kw)
+    exp = orc.demux(text, barcodes, m)
+    assert got["bad"] is None and not (got["status"] & gpu["ffi"].ST_ERROR_MASK)
+    assert got["assign"].tolist() == exp["assign"].tolist()
+    assert got["bin_count"].tolist() == exp["bin_count"].tolist()
+    assert got["spans"][:, 0].tolist() == exp["recs"]["rec_off"].tolist()
+    assert got["spans"][:, 1].tolist() == exp["recs"]["rec_end"].tolist()
+    for b in range(len(barcodes) + 1):
+        seg = exp["order"][exp["bin_start"][b]:exp["bin_start"][b + 1]]
+        assert got["per_bin"][b].tolist() == seg.tolist()
+    return got, exp
+
+
+# ---- generator: device bytes == host bytes ---------------------------------------------------------
+@pytest.mark.parametrize("name", ["cfg3", "cfg4", "cfg5"])
+def test_synth_device_equals_host(gpu, name):
+    torch, synth = gpu["torch"], gpu["synth"]
+    w = synth.WORKLOADS[name]
+    tab = synth.table(w)
+    n, first = 5000, 123456789
+    for mate in ((0, 1) if w.paired else (0,)):
+        host = synth.reads_host(w, tab, first, n, mate)
+        dev = torch.empty(n * w.rec_bytes + 64, dtype=torch.uint8, device="cuda")
+        synth.reads_device(w, tab, first, n, dev.data_ptr(), mate=mate)
+        assert np.array_equal(dev[: n * w.rec_bytes].cpu().numpy(), host)
+
+
+# ---- the first-match LUT is the oracle's find() over every possible prefix -------------------------
+@pytest.mark.parametrize("k,n,m", [(4, 7, 1), (6, 40, 2), (8, 96, 1), (5, 9, 0)])
+def test_lut_equals_first_match_over_all_prefixes(gpu, k, n, m):
+    rng = random.Random(k * 1000 + n)
+    bcs = [bytes(rng.choice(b"ACGT") for _ in range(k)) for _ in range(n)]
+    bcs[-1] = bcs[0]  # a duplicate row: the earlier row must win
+    with gpu["demux"].Demux(bcs, m, fmt=2, batch_bytes=1 << 20) as dm:
+        lut = dm.lut()
+    assert lut is not None and lut.size == 4 ** k
+    idx = np.arange(4 ** k, dtype=np.uint32)
+    code2base = np.frombuffer(b"ACTG", dtype=np.uint8)  # code = (ascii >> 1) & 3
+    pref = np.stack([code2base[(idx >> (2 * j)) & 3] for j in range(k)], 1)
+    tab = np.frombuffer(b"".join(bcs), dtype=np.uint8).reshape(n, k)
+    mism = (pref[:, None, :] != tab[None, :, :]).sum(-1)
+    ok = mism <= m
+    exp = np.where(ok.any(1), ok.argmax(1), n).astype(np.uint16)
+    assert np.array_equal(lut, exp)
+
+
+# ---- synthetic slices of the BASELINE shapes ---------------------------------------------------------
+@pytest.mark.parametrize("name,n", [("cfg3", 60000), ("cfg4", 40000), ("cfg5", 50000)])
+@pytest.mark.parametrize("flags", [0, 1])  # LUT and the plain XOR+popc table walk
+def test_synthetic_slice_parity(gpu, name, n, flags):
+    synth = gpu["synth"]
+    w = synth.WORKLOADS[name]
+    tab = synth.table(w)
+    bcs = [bytes(r) for r in tab]
+    for mate in ((0, 1) if w.paired else (0,)):
+        text = synth.reads_host(w, tab, 777, n, mate).tobytes()
+        got, exp = _check_against_oracle(gpu, text, bcs, w.mismatch, batch_bytes=4 << 20, flags=flags)
+        assert got["bin_count"].sum() == n
+
+
+def test_device_resident_batch_equals_oracle(gpu):
+    """sbr_demux_device on HBM-resident text (the benchmark path)"""
+    torch, synth, dmx = gpu["torch"], gpu["synth"], gpu["demux"]
+    w = synth.CFG3
+    tab = synth.table(w)
+    n = 200_000
+    dev = torch.empty(n * w.rec_bytes + 64, dtype=torch.uint8, device="cuda")
+    synth.reads_device(w, tab, 0, n, dev.data_ptr())
+    text = dev[: n * w.rec_bytes].cpu().numpy()
+    bcs = [bytes(r) for r in tab]
+    with dmx.Demux(bcs, w.mismatch, fmt=2, batch_bytes=n * w.rec_bytes + 4096) as dm:
+        dm.demux_device(0, dev.data_ptr(), n * w.rec_bytes, final=True, stream=torch.cuda.current_stream().cuda_stream)
+        b = dm.wait(0)
+    exp = orc.demux(text, bcs, w.mismatch)
+    assert b.n_records == n and b.consumed == n * w.rec_bytes and b.status == 0
+    assert np.array_equal(b.assign, exp["assign"])
+    assert np.array_equal(b.bin_count, exp["bin_count"])
+    assert np.array_equal(b.bin_start, exp["bin_start"])
+    assert np.array_equal(b.order, exp["order"])
+    assert np.array_equal(b.rec_off[:-1].astype(np.uint64), exp["recs"]["rec_off"])
+
+
+# ---- the in-tree fixtures (SURVEY 8c goldens) -------------------------------------------------------
+R1_GOLD = ["90d9764b8b69432c", "dd06fd51837741d1", "98a7be33c3ac7170", "5af261ae384d0e8d", "cf6171f02f1974ce",
+           "8a8208327d1ba4cc", "d88301f0531c93a4", "9e490c81cc82b11e", "88d17addc88d6666", "5a32eafb431d020f"]
+
+
+def _outputs(gpu, text, got, n_bins):
+    outs = []
+    for b in range(n_bins):
+        outs.append(b"".join(text[int(s):int(e)] for s, e in got["spans"][got["per_bin"][b].astype(np.int64)]))
+    return outs
+
+
+@pytest.mark.parametrize("m", [0, 1, 2])
+def test_reads_1_fixture(gpu, reads_1, m):
+    bcs = _bcs("bc_se.txt")
+    got, exp = _check_against_oracle(gpu, reads_1, bcs, m, batch_bytes=1 << 20)
+    outs = _outputs(gpu, reads_1, got, len(bcs) + 1)
+    assert outs == orc.demux_outputs(reads_1, bcs, m)
+    if m == 0:
+        assert [hashlib.sha256(o).hexdigest()[:16] for o in outs[:-1]] == R1_GOLD
+        assert got["bin_count"].tolist() == [1000] + [999] * 9 + [0]
+
+
+def test_test_fq_fixture(gpu):
+    text = fixture_bytes("test.fq")
+    got, _ = _check_against_oracle(gpu, text, _bcs("bc_se.txt"), 0, batch_bytes=1 << 16)
+    outs = _outputs(gpu, text, got, 11)
+    assert all(o == b"" for o in outs[:10]) and outs[10] == text
+    got, _ = _check_against_oracle(gpu, text, [b"ACCGTA", b"ATTGTT"], 1, batch_bytes=1 << 16)
+    assert got["assign"].tolist() == [0, 1, 2]
+
+
+# ---- parser edge cases --------------------------------------------------------------------------------
+def _rand_fastq(rng, n, crlf=False, plus_id=False, final_nl=True, lo=6, hi=60, alphabet=b"ACGTN"):
+    nl = b"\r\n" if crlf else b"\n"
+    out = bytearray()
+    for i in range(n):
+        L = rng.randint(lo, hi)
+        s = bytes(rng.choice(alphabet) for _ in range(L))
+        q = bytes(rng.randint(33, 73) for _ in range(L))  # '@' '+' '>' all occur in qualities
+        out += b"@r%d x" % i + nl + s + nl + (b"+r%d" % i if plus_id else b"+") + nl + q + nl
+    if not final_nl:
+        out = out[:-len(nl)]
+    return bytes(out)
+
+
+def _rand_fasta(rng, n, width=0, crlf=False, lo=6, hi=90):
+    nl = b"\r\n" if crlf else b"\n"
+    out = bytearray()
+    for i in range(n):
+        L = rng.randint(lo, hi)
+        s = bytes(rng.choice(b"ACGT") for _ in range(L))
+        out += b">s%d desc" % i + nl
+        if width:
+            for j in range(0, L, width):
+                out += s[j:j + width] + nl
+        else:
+            out += s + nl
+    return bytes(out)
+
+
+CASES = {
+    "fq": lambda r: _rand_fastq(r, 3000),
+    "fq_crlf": lambda r: _rand_fastq(r, 3000, crlf=True),
+    "fq_plus": lambda r: _rand_fastq(r, 3000, plus_id=True),
+    "fq_nofinal": lambda r: _rand_fastq(r, 3000, final_nl=False),
+    "fq_blank_tail": lambda r: _rand_fastq(r, 500) + b"\n\n\n",
+    "fq_tiny_reads": lambda r: _rand_fastq(r, 20000, lo=4, hi=5),     # > 2048 newlines per 12 KB tile
+    "fq_long_reads": lambda r: _rand_fastq(r, 40, lo=20000, hi=60000),  # lines longer than a tile
+    "fq_lower": lambda r: _rand_fastq(r, 2000, alphabet=b"ACGTacgtNRY"),
+    "fa": lambda r: _rand_fasta(r, 4000),
+    "fa_w7": lambda r: _rand_fasta(r, 4000, width=7),
+    "fa_w3": lambda r: _rand_fasta(r, 4000, width=3),                  # the match window spans lines
+    "fa_crlf": lambda r: _rand_fasta(r, 3000, width=11, crlf=True),
+    "fa_long": lambda r: _rand_fasta(r, 30, lo=30000, hi=70000, width=60),
+    "fa_blank_tail": lambda r: _rand_fasta(r, 300) + b"\n\n",
+}
+
+
+@pytest.mark.parametrize("kind", sorted(CASES))
+@pytest.mark.parametrize("m", [0, 1])
+def test_edge_inputs(gpu, kind, m):
+    rng = random.Random(hash(kind) & 0xFFFF)
+    text = CASES[kind](rng)
+    bcs = [bytes(rng.choice(b"ACGT") for _ in range(4)) for _ in range(14)]
+    batch = (1 << 20) if "long" in kind else (1 << 16)
+    got, exp = _check_against_oracle(gpu, text, bcs, m, batch_bytes=batch, chunk=50_001)
+    # per-bin output bytes through the host writer's rule: verbatim unless flagged non-canonical
+    outs_exp = orc.demux_outputs(text, bcs, m)
+    assert sum(len(o) for o in outs_exp) > 0
+
+
+@pytest.mark.parametrize("batch", [1 << 12, 12288, 12288 + 16, 3 * 12288 - 1, 50_000])
+def test_batch_and_tile_boundaries(gpu, batch):
+    """records straddle tiles (12 KB) and batches at every alignment"""
+    rng = random.Random(batch)
+    text = _rand_fastq(rng, 2500, lo=30, hi=200)
+    bcs = [bytes(rng.choice(b"ACGT") for _ in range(6)) for _ in range(20)]
+    _check_against_oracle(gpu, text, bcs, 1, batch_bytes=batch, chunk=777)
+    text = _rand_fasta(rng, 2500, lo=30, hi=200, width=50)
+    _check_against_oracle(gpu, text, bcs, 1, batch_bytes=batch, chunk=777)
+
+
+def test_ragged_and_non_acgt_tables(gpu):
+    rng = random.Random(5)
+    text = _rand_fastq(rng, 3000, alphabet=b"ACGTN")
+    # ragged lengths: zip() truncation (packed path with care masks)
+    bcs = [b"ACGTAC", b"ACG", b"TTTTTTTT", b"GA", b"CCCCC"]
+    _check_against_oracle(gpu, text, bcs, 1, batch_bytes=1 << 16)
+    # non-ACGT barcode bytes: an 'N' in the table only matches an 'N' in the read (byte-exact kernel)
+    bcs = [b"ACNT", b"NNNN", b"acgt", b"TTTT"]
+    _check_against_oracle(gpu, text, bcs, 1, batch_bytes=1 << 16)
+    # long barcodes (> 16 nt) take the byte-exact kernel too
+    bcs = [bytes(rng.choice(b"ACGT") for _ in range(24)) for _ in range(10)]
+    text = _rand_fastq(rng, 2000, lo=24, hi=60)
+    _check_against_oracle(gpu, text, bcs, 3, batch_bytes=1 << 16)
+    text = _rand_fasta(rng, 2000, lo=24, hi=90, width=10)
+    _check_against_oracle(gpu, text, bcs, 3, batch_bytes=1 << 16)
+
+
+@pytest.mark.parametrize("text,code", [
+    (b"@a\nACGT\n+\nIII\n", "unequal"),
+    (b"@a\nACGT\n-\nIIII\n", "sep"),
+    (b"@a\nACGT\n+\nIIII\nXb\nACGT\n+\nIIII\n", "start"),
+    (b"@a\nACGT\n+\nIIII\n@b\nAC\n+\nII\n", "short"),
+    (b"@a\nACGT\n+\nIIII\n@b\nACGT\n+", "trunc"),
+    (b"@a\nACGT\n+\nIIII\n\n\n\n\n", "start"),
+    (b"ACGT\n", "start"),
+    (b">a\nAC\n>b\nACGT\n", "short"),
+])
+def test_parse_violations_are_reported_like_the_oracle(gpu, text, code):
+    ffi, dm = gpu["ffi"], gpu["demux"]
+    bits = {"unequal": ffi.ST_UNEQUAL_LEN, "sep": ffi.ST_INVALID_SEP, "start": ffi.ST_INVALID_START,
+            "short": ffi.ST_SHORT_READ, "trunc": ffi.ST_TRUNCATED}[code]
+    got = dm.demux_bytes(text, [b"ACGT", b"TTTT"], 0, batch_bytes=1 << 16)
+    assert got["bad"] is not None and got["bad"][1] & bits
+    with pytest.raises(orc.OracleError) as e:
+        orc.demux(text, [b"ACGT", b"TTTT"], 0)
+    if code != "start" or text[:1] in b"@>":
+        assert got["bad"][0] == e.value.record
+
+
+def test_record_capacity_overflow_is_chunked_not_lost(gpu):
+    rng = random.Random(9)
+    text = _rand_fastq(rng, 5000, lo=8, hi=12)
+    bcs = [bytes(rng.choice(b"ACGT") for _ in range(4)) for _ in range(8)]
+    _check_against_oracle(gpu, text, bcs, 0, batch_bytes=1 << 16, max_records=300)
+
+
+# ---- size-independent properties at a large size ------------------------------------------------------
+def test_large_batch_properties(gpu):
+    torch, synth, dmx = gpu["torch"], gpu["synth"], gpu["demux"]
+    w = synth.CFG3
+    tab = synth.table(w)
+    n = 2_000_000  # 642 MB of text, one batch
+    nbytes = n * w.rec_bytes
+    dev = torch.empty(nbytes + 64, dtype=torch.uint8, device="cuda")
+    synth.reads_device(w, tab, 10_000_000, n, dev.data_ptr())
+    bcs = [bytes(r) for r in tab]
+    with dmx.Demux(bcs, w.mismatch, fmt=2, batch_bytes=nbytes + 4096, max_records=n + 16) as dm:
+        dm.demux_device(0, dev.data_ptr(), nbytes, final=True)
+        b = dm.wait(0)
+    assert b.n_records == n and b.consumed == nbytes and b.status == 0
+    assert np.array_equal(b.rec_off, np.arange(n + 1, dtype=np.uint64) * w.rec_bytes)  # fixed-size records
+    assert b.bin_count.sum() == n and np.array_equal(np.bincount(b.assign, minlength=97), b.bin_count)
+    assert np.array_equal(np.cumsum(np.concatenate([[0], b.bin_count])), b.bin_start)
+    # order is the stable counting sort of assign
+    assert np.array_equal(b.order, np.argsort(b.assign, kind="stable"))
+    # a slice against the oracle
+    k = 50_000
+    text = dev[: k * w.rec_bytes].cpu().numpy()
+    assert np.array_equal(b.assign[:k], orc.demux(text, bcs, w.mismatch)["assign"])

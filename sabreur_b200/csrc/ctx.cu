@@ -496,6 +496,7 @@ extern "C" int sbr_wait(sbr_ctx* c, uint32_t slot, sbr_result* r) {
         r->rec_key = s.h_key;
     }
     CU(c, cudaStreamSynchronize(st));
+    const uint64_t consumed_eff = s.h_rec_off[n];  // in the (possibly newline-patched) device text
     if (patched_end && s.h_rec_off[n] > s.nbytes_in) {
         // the last record ends at the caller's last byte; its canonical form gains the newline
         s.h_rec_off[n] = (uint32_t)s.nbytes_in;
@@ -511,7 +512,7 @@ extern "C" int sbr_wait(sbr_ctx* c, uint32_t slot, sbr_result* r) {
             r->first_bad_flags = bits;
         }
     }
-    if (s.final_batch && r->consumed < s.nbytes_eff && !(flags & SBR_ST_REC_OVERFLOW)) {
+    if (s.final_batch && consumed_eff < s.nbytes_eff && !(flags & SBR_ST_REC_OVERFLOW)) {
         // the stream ends inside a record (blank tails were removed at submit time)
         if (!(flags & SBR_ST_ERROR_MASK)) { r->first_bad_record = n; r->first_bad_flags = SBR_ST_TRUNCATED; }
         flags |= SBR_ST_TRUNCATED;

@@ -236,7 +236,9 @@ def main():
     flags = _ffi.CFG_TIMING | (_ffi.CFG_NO_LUT if args.no_lut else 0)
     dm = demux.Demux(bcs, w.mismatch, fmt=w.fmt, device=local_rank, batch_bytes=bu * rec + 4096, n_slots=2,
                      max_records=bu + 16, flags=flags)
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.Stream()  # a real stream: handle 0 would select the slot's own stream
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
 
     def step():
         for i, (ti, off, nb) in enumerate(batches):

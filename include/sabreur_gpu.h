@@ -61,6 +61,7 @@ typedef enum {
 #define SBR_CFG_GENERIC  0x2u  /* force the byte-exact match kernel (it is selected automatically when
                                   the table holds non-ACGT bytes or bc_len > 16) */
 #define SBR_CFG_TIMING   0x4u  /* record CUDA events around every kernel: see sbr_timing_collect() */
+#define SBR_CFG_EXACT_SCAN 0x8u /* skip the region-parallel scan: always run the look-back scan */
 
 typedef struct sbr_ctx sbr_ctx;
 
@@ -92,7 +93,10 @@ typedef struct {
     const uint32_t* bin_count; /* [n_bins] */
     const uint32_t* bin_start; /* [n_bins + 1] exclusive scan of bin_count */
     const uint32_t* order;     /* [n_records] record indices grouped by bin, ascending within a bin */
-    const uint64_t* rec_key;   /* [n_records] per-record scan word (packed prefix + flags), see DESIGN.md */
+    const uint64_t* rec_key;   /* [n_records] per-record scan word (packed prefix + flags), see DESIGN.md;
+                                  NULL unless status_flags has SBR_ST_NONCANONICAL */
+    uint32_t scan_path;        /* 1: the region-parallel scan's result stood, 0: the look-back scan ran */
+    uint32_t reserved;
 } sbr_result;
 
 /* ---- life cycle ------------------------------------------------------------------------------ */
@@ -131,6 +135,11 @@ int sbr_slot_device_result(sbr_ctx* ctx, uint32_t slot, sbr_result* res_device_p
  * Returns the number of entries (4^bc_len) or 0 when the context does not use a LUT. */
 uint64_t sbr_lut_entries(const sbr_ctx* ctx);
 int sbr_lut_copy(sbr_ctx* ctx, uint16_t* host_out, uint64_t n_entries);
+
+/* Debug / test access to the region table of the slot's last region-parallel scan: eight uint32 per
+ * region {newlines, records, detected phase, flags, last_start_nl, last_start_off, 0, 0}.
+ * Returns the number of regions copied (<= max_regions) or a negative sbr_status. */
+int sbr_debug_regions(sbr_ctx* ctx, uint32_t slot, uint32_t* host_out, uint32_t max_regions);
 
 /* Per-kernel device time accumulated since the last call (SBR_CFG_TIMING): ms[0]=scan,
  * ms[1]=match, ms[2]=partition; *launches = kernel launches covered.  Synchronises the device. */

@@ -12,14 +12,14 @@ SBR_OK = 0
 ST_INVALID_START, ST_INVALID_SEP, ST_UNEQUAL_LEN, ST_SHORT_READ = 0x01, 0x02, 0x04, 0x08
 ST_TRUNCATED, ST_REC_OVERFLOW, ST_NONCANONICAL, ST_ERROR_MASK = 0x10, 0x20, 0x40, 0x1F
 FMT_AUTO, FMT_FASTA, FMT_FASTQ = 0, 1, 2
-CFG_NO_LUT, CFG_GENERIC, CFG_TIMING = 0x1, 0x2, 0x4
+CFG_NO_LUT, CFG_GENERIC, CFG_TIMING, CFG_EXACT_SCAN = 0x1, 0x2, 0x4, 0x8
 KEY_SHORT, KEY_NONCANON = 1 << 48, 1 << 49
 
 # every symbol include/sabreur_gpu.h declares
 EXPORTS = [
     "sbr_abi_version", "sbr_device_count", "sbr_create", "sbr_destroy", "sbr_last_error", "sbr_slot_buffer",
     "sbr_submit", "sbr_wait", "sbr_demux_device", "sbr_slot_device_result", "sbr_lut_entries", "sbr_lut_copy",
-    "sbr_timing_collect", "sbr_synth_table", "sbr_synth_record_bytes", "sbr_synth_host", "sbr_synth_device",
+    "sbr_debug_regions", "sbr_timing_collect", "sbr_synth_table", "sbr_synth_record_bytes", "sbr_synth_host", "sbr_synth_device",
     "sbr_dev_alloc", "sbr_dev_free", "sbr_dev_upload", "sbr_dev_download", "sbr_host_alloc_pinned",
     "sbr_host_free_pinned",
 ]
@@ -35,7 +35,8 @@ class SbrResult(C.Structure):
     _fields_ = [("batch_seq", C.c_uint64), ("consumed", C.c_uint64), ("n_records", C.c_uint32),
                 ("status_flags", C.c_uint32), ("first_bad_record", C.c_uint32), ("first_bad_flags", C.c_uint32),
                 ("fmt", C.c_uint32), ("n_bins", C.c_uint32), ("rec_off", C.c_void_p), ("assign", C.c_void_p),
-                ("bin_count", C.c_void_p), ("bin_start", C.c_void_p), ("order", C.c_void_p), ("rec_key", C.c_void_p)]
+                ("bin_count", C.c_void_p), ("bin_start", C.c_void_p), ("order", C.c_void_p), ("rec_key", C.c_void_p),
+                ("scan_path", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class SbrSynthSpec(C.Structure):
@@ -70,6 +71,7 @@ def load():
         "sbr_slot_device_result": (i32, [vp, u32, C.POINTER(SbrResult)]),
         "sbr_lut_entries": (u64, [vp]),
         "sbr_lut_copy": (i32, [vp, vp, u64]),
+        "sbr_debug_regions": (i32, [vp, u32, vp, u32]),
         "sbr_timing_collect": (i32, [vp, C.POINTER(C.c_double * 3), C.POINTER(u64), C.POINTER(u64)]),
         "sbr_synth_table": (i32, [u64, u32, u32, u32, vp]),
         "sbr_synth_record_bytes": (u32, [C.POINTER(SbrSynthSpec)]),

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libsabreur_gpu.so")
-SOURCES = ["ctx.cu", "k_scan.cu", "k_match.cu", "k_partition.cu", "k_synth.cu"]
+SOURCES = ["ctx.cu", "k_scan.cu", "k_scan_fast.cu", "k_match.cu", "k_partition.cu", "k_synth.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math", "-diag-suppress", "177"]
 

@@ -8,26 +8,38 @@
 #include <string>
 #include <vector>
 
-#include "sbr_common.cuh"
+#include "scan_common.cuh"
 
 namespace sbr {
-// k_scan.cu
+// k_scan.cu (look-back scan: exact fallback)
 size_t scan_smem_bytes();
 cudaError_t scan_prepare(int device, int* grid_out);
 cudaError_t scan_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbytes, uint32_t max_records, uint32_t bc_len,
-                        uint32_t packed, uint32_t final_batch, BatchHeader* hdr, uint4* desc, uint32_t* rec_off,
-                        uint64_t* key, int grid_cap, cudaStream_t stream);
+                        uint32_t packed, uint32_t final_batch, uint32_t gated, BatchHeader* hdr, uint4* desc,
+                        uint32_t* rec_off, uint64_t* key, int grid_cap, cudaStream_t stream);
 uint32_t scan_tiles(uint32_t nbytes);
+// k_scan_fast.cu (region-parallel scan)
+cudaError_t scan_fast_prepare(int device, int* grid_out);
+uint32_t scan_fast_regions(uint32_t nbytes, int max_regions, uint32_t* tiles_per_region, uint32_t* extra_regions);
+cudaError_t scan_fast_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbytes, uint32_t max_records, uint32_t cap_r,
+                             uint32_t n_regions, uint32_t tiles_per_region, uint32_t extra_regions, uint32_t bc_len,
+                             uint32_t packed, uint32_t final_batch, BatchHeader* hdr, RegionInfo* info, uint32_t* region_base,
+                             uint32_t* seg_rec_off, uint64_t* seg_key, uint32_t* rec_off_dense, cudaStream_t stream);
 // k_match.cu
+struct MatchLaunch {
+    const uint64_t* key_dense; const uint64_t* seg_key; const uint32_t* seg_rec_off; const uint32_t* region_base;
+    uint32_t cap_r;
+    const BatchHeader* hdr;
+    const uint2* tab; const uint16_t* lut; const uint8_t* rows; const uint32_t* lens;
+    uint32_t n, m, k, stride;
+    const uint8_t* text; uint32_t nbytes;
+    uint16_t* assign; uint32_t* rec_off; uint64_t* key_out; uint32_t* cnt; uint32_t nbins;
+    int grid;
+};
+size_t match_smem(uint32_t n, uint32_t stride, uint32_t nbins, bool generic);
 cudaError_t match_prepare();
 cudaError_t match_build_lut(const uint2* d_tab, uint32_t n, uint32_t m, uint32_t k, uint16_t* d_lut, cudaStream_t stream);
-cudaError_t match_launch_packed(const uint64_t* d_key, const BatchHeader* d_hdr, const uint2* d_tab, uint32_t n,
-                                uint32_t m, uint32_t k, const uint16_t* d_lut, uint16_t* d_assign, uint32_t max_records,
-                                int sms, cudaStream_t stream);
-size_t match_generic_smem(uint32_t n, uint32_t stride);
-cudaError_t match_launch_generic(const uint8_t* d_text, uint32_t nbytes, const uint64_t* d_key, const BatchHeader* d_hdr,
-                                 const uint8_t* d_rows, const uint32_t* d_lens, uint32_t n, uint32_t stride, uint32_t k,
-                                 uint32_t m, uint16_t* d_assign, uint32_t max_records, int sms, cudaStream_t stream);
+cudaError_t match_launch(const MatchLaunch& L, cudaStream_t stream);
 // k_partition.cu
 struct PartitionPlan {
     int grid;
@@ -63,6 +75,10 @@ struct Slot {
     uint32_t* d_bin_count = nullptr;
     uint32_t* d_bin_start = nullptr;
     uint32_t* d_order = nullptr;
+    RegionInfo* d_info = nullptr;
+    uint32_t* d_region_base = nullptr;
+    uint32_t* d_seg_rec_off = nullptr;
+    uint64_t* d_seg_key = nullptr;
     // pinned host
     uint8_t* h_text = nullptr;
     BatchHeader* h_hdr = nullptr;
@@ -93,6 +109,8 @@ struct sbr_ctx {
     int device = 0;
     int sms = 0;
     int scan_grid = 0;
+    int fast_grid = 0;   // CTAs (= regions at most) of the region-parallel scan
+    bool exact_only = false;
     uint32_t nbins = 0;
     uint32_t max_records = 0;
     uint32_t max_tiles = 0;
@@ -150,6 +168,7 @@ extern "C" const char* sbr_last_error(const sbr_ctx* ctx) { return ctx ? ctx->er
 static void free_slot(Slot& s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFree(s.d_text); cudaFree(s.d_hdr); cudaFree(s.d_desc); cudaFree(s.d_rec_off); cudaFree(s.d_key);
+    cudaFree(s.d_info); cudaFree(s.d_region_base); cudaFree(s.d_seg_rec_off); cudaFree(s.d_seg_key);
     cudaFree(s.d_assign); cudaFree(s.d_cnt); cudaFree(s.d_bin_count); cudaFree(s.d_bin_start); cudaFree(s.d_order);
     cudaFreeHost(s.h_text); cudaFreeHost(s.h_hdr); cudaFreeHost(s.h_rec_off); cudaFreeHost(s.h_key);
     cudaFreeHost(s.h_assign); cudaFreeHost(s.h_bin_count); cudaFreeHost(s.h_bin_start); cudaFreeHost(s.h_order);
@@ -211,9 +230,12 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
     c->timing = (cfg->flags & SBR_CFG_TIMING) != 0;
 
     CU(c, scan_prepare(cfg->device, &c->scan_grid));
+    CU(c, scan_fast_prepare(cfg->device, &c->fast_grid));
+    c->exact_only = (cfg->flags & SBR_CFG_EXACT_SCAN) != 0;
     CU(c, match_prepare());
     CU(c, partition_prepare());
     c->plan = partition_plan(c->nbins, c->max_records, c->sms);
+    if (match_smem(n, k, c->nbins, !c->packed) > 200 * 1024) return fail(c, SBR_E_UNSUPPORTED, "barcode table too large");
 
     if (c->packed) {
         std::vector<uint2> tab(n);
@@ -234,7 +256,6 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
             CU(c, cudaDeviceSynchronize());
         }
     } else {
-        if (match_generic_smem(n, k) > 200 * 1024) return fail(c, SBR_E_UNSUPPORTED, "barcode table too large");
         CU(c, cudaMalloc(&c->d_rows, (size_t)n * k));
         CU(c, cudaMemcpy(c->d_rows, c->rows.data(), (size_t)n * k, cudaMemcpyHostToDevice));
         CU(c, cudaMalloc(&c->d_lens, n * sizeof(uint32_t)));
@@ -255,6 +276,11 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
         CU(c, cudaMalloc(&s.d_bin_count, c->nbins * sizeof(uint32_t)));
         CU(c, cudaMalloc(&s.d_bin_start, (c->nbins + 1) * sizeof(uint32_t)));
         CU(c, cudaMalloc(&s.d_order, (mr + 1) * sizeof(uint32_t)));
+        CU(c, cudaMalloc(&s.d_info, MAX_REGIONS * sizeof(RegionInfo)));
+        CU(c, cudaMalloc(&s.d_region_base, (MAX_REGIONS + 1) * sizeof(uint32_t)));
+        const size_t seg = mr * 5 / 4 + 65 * (size_t)MAX_REGIONS;
+        CU(c, cudaMalloc(&s.d_seg_rec_off, seg * sizeof(uint32_t)));
+        CU(c, cudaMalloc(&s.d_seg_key, seg * sizeof(uint64_t)));
         CU(c, cudaMallocHost(&s.h_hdr, sizeof(BatchHeader)));
         CU(c, cudaMallocHost(&s.h_bin_count, c->nbins * sizeof(uint32_t)));
         CU(c, cudaMallocHost(&s.h_bin_start, (c->nbins + 1) * sizeof(uint32_t)));
@@ -316,19 +342,37 @@ static int launch_pipeline(sbr_ctx* c, Slot& s, const uint8_t* d_text, uint32_t 
     CU(c, cudaMemsetAsync(s.d_hdr, 0, sizeof(BatchHeader), st));
     CU(c, cudaMemsetAsync(s.d_desc, 0, (size_t)scan_tiles(nbytes) * sizeof(uint4), st));
     if (ev) CU(c, cudaEventRecord(ev[0], st));
+    uint32_t cap_r = 0;
+    if (!c->exact_only) {
+        uint32_t tpr = 0, extra = 0;
+        uint32_t nreg = scan_fast_regions(nbytes, c->fast_grid, &tpr, &extra);
+        // segments get 25 % + 64 records of slack over an even split: regions hold unequal record counts
+        cap_r = (uint32_t)(((uint64_t)c->max_records * 5 / 4) / nreg) + 64;
+        CU(c, scan_fast_launch(fmt, d_text, nbytes, c->max_records, cap_r, nreg, tpr, extra, c->cfg.bc_len, c->packed ? 1u : 0u,
+                               (uint32_t)final_batch, s.d_hdr, s.d_info, s.d_region_base, s.d_seg_rec_off, s.d_seg_key,
+                               s.d_rec_off, st));
+        c->launches += 2;
+    }
+    // the look-back scan: unconditional when forced, otherwise it returns at once unless the fast scan gave up
     CU(c, scan_launch(fmt, d_text, nbytes, c->max_records, c->cfg.bc_len, c->packed ? 1u : 0u, (uint32_t)final_batch,
-                      s.d_hdr, s.d_desc, s.d_rec_off, s.d_key, c->scan_grid, st));
+                      c->exact_only ? 0u : 1u, s.d_hdr, s.d_desc, s.d_rec_off, s.d_key, c->scan_grid, st));
     if (ev) CU(c, cudaEventRecord(ev[1], st));
-    if (c->packed)
-        CU(c, match_launch_packed(s.d_key, s.d_hdr, c->d_tab, c->cfg.n_barcodes, c->cfg.mismatch, c->cfg.bc_len, c->d_lut,
-                                  s.d_assign, c->max_records, c->sms, st));
-    else
-        CU(c, match_launch_generic(d_text, nbytes, s.d_key, s.d_hdr, c->d_rows, c->d_lens, c->cfg.n_barcodes,
-                                   c->cfg.bc_len, c->cfg.bc_len, c->cfg.mismatch, s.d_assign, c->max_records, c->sms, st));
+    {
+        MatchLaunch L{};
+        L.key_dense = s.d_key; L.seg_key = s.d_seg_key; L.seg_rec_off = s.d_seg_rec_off; L.region_base = s.d_region_base;
+        L.cap_r = cap_r;
+        L.hdr = s.d_hdr;
+        L.tab = c->packed ? c->d_tab : nullptr; L.lut = c->d_lut; L.rows = c->d_rows; L.lens = c->d_lens;
+        L.n = c->cfg.n_barcodes; L.m = c->cfg.mismatch; L.k = c->cfg.bc_len; L.stride = c->cfg.bc_len;
+        L.text = d_text; L.nbytes = nbytes;
+        L.assign = s.d_assign; L.rec_off = s.d_rec_off; L.key_out = s.d_key; L.cnt = s.d_cnt; L.nbins = c->nbins;
+        L.grid = c->plan.grid;
+        CU(c, match_launch(L, st));
+    }
     if (ev) CU(c, cudaEventRecord(ev[2], st));
     CU(c, partition_launch(s.d_assign, s.d_hdr, c->nbins, s.d_cnt, s.d_bin_count, s.d_bin_start, s.d_order, c->plan, st));
     if (ev) CU(c, cudaEventRecord(ev[3], st));
-    c->launches += 2 /*memsets*/ + (fmt == SBR_FMT_FASTA ? 2 : 1) + 1 + 4;
+    c->launches += (fmt == SBR_FMT_FASTA ? 2 : 1) + 1 + 3;  // look-back scan (+finish), match, partition
     return SBR_OK;
 }
 
@@ -481,6 +525,7 @@ extern "C" int sbr_wait(sbr_ctx* c, uint32_t slot, sbr_result* r) {
     const uint32_t n = H.n_records;
     r->n_records = n;
     r->fmt = H.fmt ? H.fmt : s.fmt;
+    r->scan_path = H.mode;
     // second phase: the per-record arrays at their exact size
     CU(c, cudaMemcpyAsync(s.h_rec_off, s.d_rec_off, ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     if (n) {
@@ -520,6 +565,15 @@ extern "C" int sbr_wait(sbr_ctx* c, uint32_t slot, sbr_result* r) {
     if (r->consumed > s.nbytes_in) r->consumed = s.nbytes_in;  // the supplied final newline is not the caller's byte
     r->status_flags = flags;
     return SBR_OK;
+}
+
+extern "C" int sbr_debug_regions(sbr_ctx* c, uint32_t slot, uint32_t* host_out, uint32_t max_regions) {
+    if (!c || slot >= c->slots.size() || !host_out) return fail(c, SBR_E_INVALID_ARG, "bad argument");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaDeviceSynchronize());
+    uint32_t n = max_regions < (uint32_t)MAX_REGIONS ? max_regions : (uint32_t)MAX_REGIONS;
+    CU(c, cudaMemcpy(host_out, c->slots[slot].d_info, (size_t)n * sizeof(RegionInfo), cudaMemcpyDeviceToHost));
+    return (int)n;
 }
 
 extern "C" uint64_t sbr_lut_entries(const sbr_ctx* c) { return c ? c->lut_entries : 0; }

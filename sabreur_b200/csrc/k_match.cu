@@ -12,7 +12,7 @@
 // first-match lookup table (built by the same XOR+popc routine over all 4^k keys) and the per-read
 // work becomes one L1/L2 gather; reads with invalid bases still take the table walk.
 // Generic path (non-ACGT barcode bytes or bc_len > 16): byte-exact compare on the raw text.
-#include "sbr_common.cuh"
+#include "scan_common.cuh"
 
 namespace sbr {
 
@@ -49,74 +49,110 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_build_lut(const uint2* __rest
         lut[idx] = (uint16_t)first_match(s_tab, n, m, idx, 0u);
 }
 
-template <bool USE_LUT>
-__global__ void __launch_bounds__(MATCH_THREADS) k_match_packed(const uint64_t* __restrict__ key,
-                                                                const BatchHeader* __restrict__ hdr,
-                                                                const uint2* __restrict__ g_tab, uint32_t n, uint32_t m,
-                                                                uint32_t code_mask, const uint16_t* __restrict__ lut,
-                                                                uint16_t* __restrict__ assign) {
-    extern __shared__ uint2 s_tab[];
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_tab[i] = g_tab[i];
-    __syncthreads();
-    const uint32_t nrec = hdr->n_records;
-    auto one = [&](uint64_t k) -> uint32_t {
-        uint32_t codes = (uint32_t)k & code_mask;
-        uint32_t inval = (uint32_t)(k >> 32) & 0xFFFFu;
-        if (k & KEY_SHORT) return n;  // reported by the scan; the host aborts like the reference's panic
-        if (USE_LUT && inval == 0) return __ldg(lut + codes);
-        return first_match(s_tab, n, m, codes, spread16(inval));
-    };
-    // four reads per thread: 2 x 16-byte key loads, one 8-byte store
-    const uint32_t quads = nrec >> 2;
-    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
-        const uint4* kp = reinterpret_cast<const uint4*>(key + 4ull * q);
-        uint4 a = __ldg(kp), b = __ldg(kp + 1);
-        uint32_t r0 = one(((uint64_t)a.y << 32) | a.x), r1 = one(((uint64_t)a.w << 32) | a.z);
-        uint32_t r2 = one(((uint64_t)b.y << 32) | b.x), r3 = one(((uint64_t)b.w << 32) | b.z);
-        reinterpret_cast<uint2*>(assign)[q] = make_uint2(r0 | (r1 << 16), r2 | (r3 << 16));
-    }
-    if (blockIdx.x == 0) {
-        uint32_t i = (quads << 2) + threadIdx.x;
-        if (i < nrec) assign[i] = (uint16_t)one(key[i]);
-    }
+// Where record g of the batch lives.  mode 1 (fast scan): per-region segments, found by a binary search
+// over the regions' exclusive record prefix; mode 0 (look-back scan): dense arrays.
+struct RecSource {
+    const uint64_t* key_dense;
+    const uint64_t* seg_key;
+    const uint32_t* seg_rec_off;
+    const uint32_t* region_base;  // [n_regions + 1]
+    uint32_t cap_r;
+};
+
+// records [lo, hi) of warp-slice v out of V: equal contiguous chunks, multiple of 32 (same as k_partition.cu)
+__device__ __forceinline__ void slice_range(uint32_t n, uint32_t V, uint32_t v, uint32_t& lo, uint32_t& hi) {
+    uint32_t per = (n + V - 1) / V;
+    per = (per + 31u) & ~31u;
+    uint64_t a = (uint64_t)per * v, b = a + per;
+    lo = a < n ? (uint32_t)a : n;
+    hi = b < n ? (uint32_t)b : n;
 }
 
-// byte-exact path: key[31:0] = batch offset of the first sequence byte
-__global__ void __launch_bounds__(MATCH_THREADS) k_match_generic(const uint8_t* __restrict__ text, uint32_t nbytes,
-                                                                 const uint64_t* __restrict__ key,
-                                                                 const BatchHeader* __restrict__ hdr,
-                                                                 const uint8_t* __restrict__ g_rows,
-                                                                 const uint32_t* __restrict__ g_lens, uint32_t n,
-                                                                 uint32_t stride, uint32_t k, uint32_t m,
-                                                                 uint16_t* __restrict__ assign) {
-    extern __shared__ uint8_t s_raw[];
-    uint8_t* rows = s_raw;
-    uint32_t* lens = reinterpret_cast<uint32_t*>(s_raw + (((size_t)n * stride + 3) & ~(size_t)3));
-    for (uint32_t i = threadIdx.x; i < n * stride; i += blockDim.x) rows[i] = g_rows[i];
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) lens[i] = min(g_lens[i], k);  // zip stops at seq[..bc_len]
+// MODE 0: first-match LUT, 1: XOR+popc table walk, 2: byte-exact compare on the raw text.
+// Every warp owns a contiguous slice of the batch's records (the slices of kernel 3): it reads the
+// scan words (compacting the fast scan's per-region segments into the dense rec_off array on the way),
+// writes the assignments and counts its bins in shared memory -> cnt[bin][slice].
+template <int MODE>
+__global__ void __launch_bounds__(MATCH_THREADS) k_match(RecSource src, const BatchHeader* __restrict__ hdr,
+                                                         const uint2* __restrict__ g_tab, uint32_t n, uint32_t m,
+                                                         uint32_t code_mask, const uint16_t* __restrict__ lut,
+                                                         const uint8_t* __restrict__ text, uint32_t nbytes,
+                                                         const uint8_t* __restrict__ g_rows,
+                                                         const uint32_t* __restrict__ g_lens, uint32_t stride, uint32_t k,
+                                                         uint16_t* __restrict__ assign, uint32_t* __restrict__ rec_off,
+                                                         uint64_t* __restrict__ key_out, uint32_t* __restrict__ cnt,
+                                                         uint32_t nbins) {
+    extern __shared__ __align__(16) uint8_t s_mem[];
+    // layout: [warps][nbins] histogram | region_base copy | table
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_mem);
+    constexpr int WARPS = MATCH_THREADS / 32;
+    uint32_t* s_base = s_hist + (size_t)WARPS * nbins;
+    const uint32_t mode = hdr->mode, nreg = mode ? hdr->n_regions : 0u;
+    uint8_t* s_tab_raw = reinterpret_cast<uint8_t*>(s_base + MAX_REGIONS + 2);  // even word count: uint2 rows stay 8-byte aligned
+    uint2* s_tab = reinterpret_cast<uint2*>(s_tab_raw);
+    uint8_t* s_rows = s_tab_raw;
+    uint32_t* s_lens = reinterpret_cast<uint32_t*>(s_tab_raw + (((size_t)n * stride + 3) & ~(size_t)3));
+    if (MODE == 2) {
+        for (uint32_t i = threadIdx.x; i < n * stride; i += blockDim.x) s_rows[i] = g_rows[i];
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_lens[i] = min(g_lens[i], k);  // zip stops at seq[..bc_len]
+    } else {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_tab[i] = g_tab[i];
+    }
+    for (uint32_t i = threadIdx.x; i <= nreg; i += blockDim.x) s_base[i] = src.region_base[i];
+    for (uint32_t i = threadIdx.x; i < WARPS * nbins; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     const uint32_t nrec = hdr->n_records;
     const bool fasta = hdr->fmt == SBR_FMT_FASTA;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += gridDim.x * blockDim.x) {
-        uint64_t kk = key[i];
-        uint32_t hit = n;
-        if (!(kk & KEY_SHORT)) {
-            uint8_t pre[64];
-            uint32_t q = (uint32_t)kk, got = 0;
-            while (got < k && q < nbytes) {  // FASTA sequences may wrap lines inside the window
-                uint8_t c = text[q++];
-                if (fasta && (c == '\n' || (c == '\r' && q < nbytes && text[q] == '\n'))) continue;
-                pre[got++] = c;
+    // the host asks for the per-record scan words only when some record needs re-serialisation
+    const bool want_keys = mode && (hdr->status & SBR_ST_NONCANONICAL);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t V = gridDim.x * WARPS, v = blockIdx.x * WARPS + warp;
+    uint32_t* mine = s_hist + (size_t)warp * nbins;
+    uint32_t lo, hi;
+    slice_range(nrec, V, v, lo, hi);
+    for (uint32_t g = lo + lane; g < hi; g += 32) {
+        uint64_t kk;
+        if (mode) {
+            uint32_t a = 0, b = nreg;  // largest c with s_base[c] <= g
+            while (b - a > 1) {
+                uint32_t mid = (a + b) >> 1;
+                if (s_base[mid] <= g) a = mid; else b = mid;
             }
-            for (uint32_t b = 0; b < n && hit == n; ++b) {
-                const uint8_t* row = rows + (size_t)b * stride;
-                uint32_t mis = 0;
-                for (uint32_t j = 0; j < lens[b]; ++j) mis += (row[j] != pre[j]);
-                if (mis <= m) hit = b;
+            size_t at = (size_t)a * src.cap_r + (g - s_base[a]);
+            kk = src.seg_key[at];
+            rec_off[g] = src.seg_rec_off[at];
+            if (want_keys) key_out[g] = kk;
+        } else {
+            kk = src.key_dense[g];
+        }
+        uint32_t hit = n;
+        if (!(kk & KEY_SHORT)) {  // short reads are reported by the scan; the host aborts like the reference's panic
+            if (MODE == 2) {
+                uint8_t pre[64];
+                uint32_t q = (uint32_t)kk, got = 0;
+                while (got < k && q < nbytes) {  // FASTA sequences may wrap lines inside the window
+                    uint8_t c = text[q++];
+                    if (fasta && (c == '\n' || (c == '\r' && q < nbytes && text[q] == '\n'))) continue;
+                    pre[got++] = c;
+                }
+                for (uint32_t b = 0; b < n && hit == n; ++b) {
+                    const uint8_t* row = s_rows + (size_t)b * stride;
+                    uint32_t mis = 0;
+                    for (uint32_t j = 0; j < s_lens[b]; ++j) mis += (row[j] != pre[j]);
+                    if (mis <= m) hit = b;
+                }
+            } else {
+                uint32_t codes = (uint32_t)kk & code_mask;
+                uint32_t inval = (uint32_t)(kk >> 32) & 0xFFFFu;
+                if (MODE == 0 && inval == 0) hit = __ldg(lut + codes);
+                else hit = first_match(s_tab, n, m, codes, spread16(inval));
             }
         }
-        assign[i] = (uint16_t)hit;
+        assign[g] = (uint16_t)hit;
+        atomicAdd(&mine[hit], 1u);
     }
+    __syncwarp();
+    for (uint32_t b = lane; b < nbins; b += 32) cnt[(size_t)b * V + v] = mine[b];
 }
 
 }  // namespace
@@ -129,40 +165,47 @@ cudaError_t match_build_lut(const uint2* d_tab, uint32_t n, uint32_t m, uint32_t
     return cudaGetLastError();
 }
 
-cudaError_t match_launch_packed(const uint64_t* d_key, const BatchHeader* d_hdr, const uint2* d_tab, uint32_t n,
-                                uint32_t m, uint32_t k, const uint16_t* d_lut, uint16_t* d_assign, uint32_t max_records,
-                                int sms, cudaStream_t stream) {
-    uint32_t code_mask = k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
-    uint32_t want = (max_records / 4 + MATCH_THREADS - 1) / MATCH_THREADS;
-    int grid = (int)max(1u, min(want, (uint32_t)sms * 8u));
-    size_t smem = n * sizeof(uint2);
-    if (d_lut)
-        k_match_packed<true><<<grid, MATCH_THREADS, smem, stream>>>(d_key, d_hdr, d_tab, n, m, code_mask, d_lut, d_assign);
-    else
-        k_match_packed<false><<<grid, MATCH_THREADS, smem, stream>>>(d_key, d_hdr, d_tab, n, m, code_mask, nullptr,
-                                                                      d_assign);
-    return cudaGetLastError();
+struct MatchLaunch {
+    // sources
+    const uint64_t* key_dense; const uint64_t* seg_key; const uint32_t* seg_rec_off; const uint32_t* region_base;
+    uint32_t cap_r;
+    const BatchHeader* hdr;
+    // table
+    const uint2* tab; const uint16_t* lut; const uint8_t* rows; const uint32_t* lens;
+    uint32_t n, m, k, stride;
+    const uint8_t* text; uint32_t nbytes;
+    // outputs
+    uint16_t* assign; uint32_t* rec_off; uint64_t* key_out; uint32_t* cnt; uint32_t nbins;
+    int grid;  // = the partition plan's grid: the histogram slices are kernel 3's slices
+};
+
+size_t match_smem(uint32_t n, uint32_t stride, uint32_t nbins, bool generic) {
+    size_t tab = generic ? ((((size_t)n * stride + 3) & ~(size_t)3) + n * 4u) : (size_t)n * sizeof(uint2);
+    return (size_t)(MATCH_THREADS / 32) * nbins * 4u + (MAX_REGIONS + 2) * 4u + tab + 16;
 }
 
-size_t match_generic_smem(uint32_t n, uint32_t stride) { return (((size_t)n * stride + 3) & ~(size_t)3) + n * 4u; }
-
 cudaError_t match_prepare() {
-    cudaError_t e = cudaFuncSetAttribute(k_match_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_match_packed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_match_packed<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-    if (e != cudaSuccess) return e;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_match<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_match<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_match<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_build_lut, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
 }
 
-cudaError_t match_launch_generic(const uint8_t* d_text, uint32_t nbytes, const uint64_t* d_key, const BatchHeader* d_hdr,
-                                 const uint8_t* d_rows, const uint32_t* d_lens, uint32_t n, uint32_t stride, uint32_t k,
-                                 uint32_t m, uint16_t* d_assign, uint32_t max_records, int sms, cudaStream_t stream) {
-    uint32_t want = (max_records + MATCH_THREADS - 1) / MATCH_THREADS;
-    int grid = (int)max(1u, min(want, (uint32_t)sms * 4u));
-    k_match_generic<<<grid, MATCH_THREADS, match_generic_smem(n, stride), stream>>>(d_text, nbytes, d_key, d_hdr, d_rows,
-                                                                                    d_lens, n, stride, k, m, d_assign);
+cudaError_t match_launch(const MatchLaunch& L, cudaStream_t stream) {
+    RecSource src{L.key_dense, L.seg_key, L.seg_rec_off, L.region_base, L.cap_r};
+    const bool generic = L.tab == nullptr;
+    uint32_t code_mask = L.k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * L.k)) - 1u);
+    size_t smem = match_smem(L.n, L.stride, L.nbins, generic);
+    if (generic)
+        k_match<2><<<L.grid, MATCH_THREADS, smem, stream>>>(src, L.hdr, nullptr, L.n, L.m, 0u, nullptr, L.text, L.nbytes, L.rows,
+                                                            L.lens, L.stride, L.k, L.assign, L.rec_off, L.key_out, L.cnt, L.nbins);
+    else if (L.lut)
+        k_match<0><<<L.grid, MATCH_THREADS, smem, stream>>>(src, L.hdr, L.tab, L.n, L.m, code_mask, L.lut, nullptr, 0u, nullptr,
+                                                            nullptr, 0u, L.k, L.assign, L.rec_off, L.key_out, L.cnt, L.nbins);
+    else
+        k_match<1><<<L.grid, MATCH_THREADS, smem, stream>>>(src, L.hdr, L.tab, L.n, L.m, code_mask, nullptr, nullptr, 0u, nullptr,
+                                                            nullptr, 0u, L.k, L.assign, L.rec_off, L.key_out, L.cnt, L.nbins);
     return cudaGetLastError();
 }
 

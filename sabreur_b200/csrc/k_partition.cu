@@ -7,8 +7,8 @@
 // order, bin_count[b] = how many.  Bin n_barcodes is "unknown".
 //
 // A stable counting sort over <= 65535 bins:
-//   k_hist    every warp owns a contiguous slice of the records and counts its bins in shared memory
-//             -> cnt[bin][slice]                                    (reads assign once, 2 B/record)
+//   (hist)    fused into the match kernel: every warp owns a contiguous slice of the records and counts
+//             its bins in shared memory while it writes the assignments -> cnt[bin][slice]
 //   k_binscan one block per bin: exclusive scan of cnt[bin][*] in place, bin totals -> bin_count
 //   k_binstart single block: exclusive scan of bin_count -> bin_start
 //   k_scatter same slices; per warp a running cursor per bin in shared memory; __match_any_sync
@@ -30,23 +30,6 @@ __device__ __forceinline__ void slice_range(uint32_t n, uint32_t V, uint32_t v, 
     uint64_t a = (uint64_t)per * v, b = a + per;
     lo = a < n ? (uint32_t)a : n;
     hi = b < n ? (uint32_t)b : n;
-}
-
-__global__ void __launch_bounds__(PART_THREADS) k_hist(const uint16_t* __restrict__ assign,
-                                                       const BatchHeader* __restrict__ hdr, uint32_t nbins,
-                                                       uint32_t* __restrict__ cnt /* [nbins][V] */) {
-    extern __shared__ uint32_t s_cnt[];  // [PART_WARPS][nbins]
-    const uint32_t n = hdr->n_records;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t V = gridDim.x * PART_WARPS, v = blockIdx.x * PART_WARPS + warp;
-    uint32_t* mine = s_cnt + (size_t)warp * nbins;
-    for (uint32_t b = lane; b < nbins; b += 32) mine[b] = 0;
-    __syncwarp();
-    uint32_t lo, hi;
-    slice_range(n, V, v, lo, hi);
-    for (uint32_t i = lo + lane; i < hi; i += 32) atomicAdd(&mine[assign[i]], 1u);
-    __syncwarp();
-    for (uint32_t b = lane; b < nbins; b += 32) cnt[(size_t)b * V + v] = mine[b];
 }
 
 // one block per bin: in-place exclusive scan over the V slices of that bin
@@ -161,15 +144,12 @@ PartitionPlan partition_plan(uint32_t nbins, uint32_t max_records, int sms) {
 }
 
 cudaError_t partition_prepare() {
-    cudaError_t e = cudaFuncSetAttribute(k_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 }
 
 cudaError_t partition_launch(const uint16_t* d_assign, const BatchHeader* d_hdr, uint32_t nbins, uint32_t* d_cnt,
                              uint32_t* d_bin_count, uint32_t* d_bin_start, uint32_t* d_order, const PartitionPlan& p,
                              cudaStream_t stream) {
-    k_hist<<<p.grid, PART_THREADS, p.smem, stream>>>(d_assign, d_hdr, nbins, d_cnt);
     k_binscan<<<nbins, PART_THREADS, 0, stream>>>(d_cnt, p.V, d_bin_count);
     k_binstart<<<1, 1024, 0, stream>>>(d_bin_count, nbins, d_bin_start);
     k_scatter<<<p.grid, PART_THREADS, p.smem, stream>>>(d_assign, d_hdr, nbins, d_cnt, d_bin_start, d_order);

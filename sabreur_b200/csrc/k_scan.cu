@@ -16,7 +16,7 @@
 //   * one thread per record (the one whose 4th newline lies in the tile) validates the record the
 //     way needletail does ('@', '+', equal lengths, CR handling), writes rec_off[r+1] and the packed
 //     2-bit prefix key[r] that kernel 2 consumes as a coalesced 8-byte stream.
-#include "sbr_common.cuh"
+#include "scan_common.cuh"
 
 namespace sbr {
 
@@ -24,8 +24,6 @@ namespace {
 
 constexpr uint32_t INVALID_TILE = 0xFFFFFFFFu;
 constexpr uint32_t DESC_AGG = 1u, DESC_INC = 2u;
-constexpr uint32_t NOPOS = 0xFFFFFFFFu;
-constexpr int GHOSTS = 4;  // list[GHOSTS + i] = i-th newline of the window; list[GHOSTS-1-g] = g-th newline before it
 
 struct ScanSmem {
     uint64_t full_bar[SCAN_STAGES];
@@ -45,40 +43,12 @@ struct ScanArgs {
     uint32_t bc_len;
     uint32_t packed;       // 1: key = packed prefix, 0: key = seq offset
     uint32_t final_batch;
+    uint32_t gated;        // 1: run only if the fast scan gave up (hdr->spec_fail)
     BatchHeader* hdr;
     uint4* desc;
     uint32_t* rec_off;
     uint64_t* key;
 };
-
-__device__ __forceinline__ void report_bad(BatchHeader* hdr, uint32_t record, uint32_t bits) {
-    atomicOr(&hdr->status, bits);
-    unsigned long long packed = ((unsigned long long)record << 8) | bits;
-    atomicMax(&hdr->first_bad_inv, ~packed);
-}
-
-// byte at batch position pos: from the staged tile when it is inside, else from global (L2)
-struct ByteSrc {
-    const uint8_t* sm;
-    const uint8_t* text;
-    uint32_t lo, hi;
-    __device__ __forceinline__ uint32_t operator()(uint32_t pos) const {
-        return (pos >= lo && pos < hi) ? sm[pos - lo] : text[pos];
-    }
-};
-
-// 2-bit pack of k bases starting at s; returns codes | invalid<<32
-__device__ __forceinline__ uint64_t pack_prefix(const ByteSrc& B, uint32_t s, uint32_t k) {
-    uint32_t codes = 0, inval = 0;
-    for (uint32_t q = 0; q < k; ++q) {
-        uint32_t c = B(s + q);
-        uint32_t code = (c >> 1) & 3u;
-        uint32_t canon = (0x47544341u >> (8 * code)) & 0xFFu;  // code 0..3 -> 'A','C','T','G'
-        codes |= code << (2 * q);
-        inval |= (uint32_t)(c != canon) << q;
-    }
-    return (uint64_t)codes | ((uint64_t)inval << 32);
-}
 
 // decoupled look-back over tile descriptors; executed by warp 0.
 // in:  own aggregate (cnt, t0,t1,t2 = own last newline positions, most recent first)
@@ -172,20 +142,6 @@ __device__ __forceinline__ uint32_t lookback_fasta(uint4* desc, uint32_t tile, u
     return base;
 }
 
-// 16-bit mask of '>' bytes in a 16-byte chunk
-__device__ __forceinline__ uint32_t gt_flags(uint32_t w) {
-    uint32_t a = (w ^ 0x3E3E3E3Eu) & 0x7F7F7F7Fu;
-    uint32_t b = a + 0x7F7F7F7Fu;
-    return ~(b | w) & 0x80808080u;
-}
-__device__ __forceinline__ uint32_t gt_mask16(uint4 v) {
-    uint32_t n0 = (gt_flags(v.x) * 0x00204081u) >> 28;
-    uint32_t n1 = (gt_flags(v.y) * 0x00204081u) >> 28;
-    uint32_t n2 = (gt_flags(v.z) * 0x00204081u) >> 28;
-    uint32_t n3 = (gt_flags(v.w) * 0x00204081u) >> 28;
-    return n0 | (n1 << 4) | (n2 << 8) | (n3 << 12);
-}
-
 // ------------------------------------------------------------------------------------------------
 // FASTQ: one thread per record whose final newline is list entry i (window-relative, may use ghosts)
 // ------------------------------------------------------------------------------------------------
@@ -193,28 +149,11 @@ __device__ __forceinline__ void fastq_record(const ScanArgs& A, const ByteSrc& B
                                              uint32_t r) {
     const uint32_t p3 = list[GHOSTS + i], p2 = list[GHOSTS + i - 1], p1 = list[GHOSTS + i - 2],
                    p0 = list[GHOSTS + i - 3];
-    // start of this record = previous record's final newline + 1 is checked by that record's thread
-    // ("next start" check below); record 0 checks byte 0 itself.
-    uint32_t bits = 0;
+    uint64_t key;
+    uint32_t bits = fastq_eval(B, p0, p1, p2, p3, A.bc_len, A.packed, key);
+    // the start of this record is checked by the previous record's thread ("next start" below);
+    // record 0 checks byte 0 itself
     if (r == 0 && B(0) != '@') bits |= SBR_ST_INVALID_START;
-    const uint32_t s = p0 + 1;
-    const uint32_t cr0 = (p0 > 0 && B(p0 - 1) == '\r') ? 1u : 0u;  // header line is never empty ('@')
-    const uint32_t cr1 = (p1 > s && B(p1 - 1) == '\r') ? 1u : 0u;
-    const uint32_t cr2 = (p2 > p1 + 1 && B(p2 - 1) == '\r') ? 1u : 0u;
-    const uint32_t cr3 = (p3 > p2 + 1 && B(p3 - 1) == '\r') ? 1u : 0u;
-    const uint32_t seq_len = (p1 - cr1) - s;
-    const uint32_t qual_len = (p3 - cr3) - (p2 + 1);
-    if (!(p1 + 1 < p2 && B(p1 + 1) == '+')) bits |= SBR_ST_INVALID_SEP;
-    if (seq_len != qual_len) bits |= SBR_ST_UNEQUAL_LEN;
-    uint64_t key = 0;
-    if (seq_len < A.bc_len) {
-        bits |= SBR_ST_SHORT_READ;
-        key |= KEY_SHORT | (A.packed ? 0ull : (uint64_t)s);
-    } else {
-        key |= A.packed ? pack_prefix(B, s, A.bc_len) : (uint64_t)s;
-    }
-    const bool sep_bare = ((p2 - cr2) - (p1 + 1)) == 1u;
-    if (cr0 | cr1 | cr2 | cr3 | (uint32_t)!sep_bare) key |= KEY_NONCANON;
     if (r < A.max_records) {
         A.rec_off[r + 1] = p3 + 1;
         A.key[r] = key;
@@ -231,41 +170,9 @@ __device__ __forceinline__ void fastq_record(const ScanArgs& A, const ByteSrc& B
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fasta_record(const ScanArgs& A, const ByteSrc& B, uint32_t start, uint32_t hend_hint,
                                              uint32_t r) {
-    // header end: first newline at or after start (hint = next list entry when known)
-    uint32_t h = hend_hint;
-    if (h == NOPOS) {
-        h = start;
-        while (h < A.nbytes && B(h) != '\n') ++h;
-    }
-    uint64_t key = 0;
-    uint32_t q = h + 1, got = 0, codes = 0, inval = 0, first_seq = NOPOS;
-    const uint32_t k = A.bc_len;
-    while (got < k) {
-        if (q >= A.nbytes) break;
-        uint32_t c = B(q);
-        if (c == '\n') {
-            if (q + 1 >= A.nbytes || B(q + 1) == '>') break;  // record ends: short read
-            ++q;
-            continue;
-        }
-        if (c == '\r' && q + 1 < A.nbytes && B(q + 1) == '\n') { ++q; continue; }
-        if (c == '\r' && q + 1 >= A.nbytes) break;
-        if (first_seq == NOPOS) first_seq = q;
-        if (A.packed) {
-            uint32_t code = (c >> 1) & 3u;
-            uint32_t canon = (0x47544341u >> (8 * code)) & 0xFFu;
-            codes |= code << (2 * got);
-            inval |= (uint32_t)(c != canon) << got;
-        }
-        ++got;
-        ++q;
-    }
-    if (got < k) {
-        key = KEY_SHORT | (A.packed ? 0ull : (uint64_t)(first_seq == NOPOS ? h + 1 : first_seq));
-        report_bad(A.hdr, r, SBR_ST_SHORT_READ);
-    } else {
-        key = A.packed ? ((uint64_t)codes | ((uint64_t)inval << 32)) : (uint64_t)first_seq;
-    }
+    uint64_t key;
+    const uint32_t why = fasta_eval(B, A.nbytes, start, hend_hint, A.bc_len, A.packed, key);
+    if (why == 1 || (why == 2 && A.final_batch)) report_bad(A.hdr, r, SBR_ST_SHORT_READ);
     if (r <= A.max_records) A.rec_off[r] = start;
     if (r < A.max_records) A.key[r] = key;
 }
@@ -277,6 +184,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan(ScanArgs A) {
     ScanSmem& S = *reinterpret_cast<ScanSmem*>(dyn_smem + SCAN_STAGES * SCAN_TILE);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t G = gridDim.x;
+    if (A.gated && A.hdr->spec_fail == 0) return;  // the fast scan's result stands
 
     auto issue = [&](int s, uint32_t tile) {  // thread 0 only
         uint32_t lo = tile * (uint32_t)SCAN_TILE;
@@ -481,7 +389,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan(ScanArgs A) {
 
 // FASTA epilogue: record count from the last inclusive descriptor; batch-level canonicity
 __global__ void k_fasta_finish(BatchHeader* hdr, const uint4* desc, uint32_t ntiles, uint32_t nbytes,
-                               uint32_t max_records, uint32_t final_batch, uint32_t* rec_off) {
+                               uint32_t max_records, uint32_t final_batch, uint32_t gated, uint32_t* rec_off) {
+    if (gated && hdr->spec_fail == 0) return;
     uint32_t starts = (ntiles ? (desc[ntiles - 1].x & 0x3FFFFFFFu) : 0u) + 1u;  // + the record at byte 0
     uint32_t complete = final_batch ? starts : starts - 1u;
     uint32_t kept = min(complete, max_records);
@@ -521,8 +430,8 @@ cudaError_t scan_prepare(int device, int* grid_out) {
 
 // Launches the scan on `stream`.  hdr must have been zeroed and desc[0..ntiles) cleared.
 cudaError_t scan_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbytes, uint32_t max_records, uint32_t bc_len,
-                        uint32_t packed, uint32_t final_batch, BatchHeader* hdr, uint4* desc, uint32_t* rec_off,
-                        uint64_t* key, int grid_cap, cudaStream_t stream) {
+                        uint32_t packed, uint32_t final_batch, uint32_t gated, BatchHeader* hdr, uint4* desc,
+                        uint32_t* rec_off, uint64_t* key, int grid_cap, cudaStream_t stream) {
     ScanArgs A;
     A.text = d_text;
     A.nbytes = nbytes;
@@ -531,6 +440,7 @@ cudaError_t scan_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbytes, ui
     A.bc_len = bc_len;
     A.packed = packed;
     A.final_batch = final_batch;
+    A.gated = gated;
     A.hdr = hdr;
     A.desc = desc;
     A.rec_off = rec_off;
@@ -542,7 +452,7 @@ cudaError_t scan_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbytes, ui
         k_scan<SBR_FMT_FASTQ><<<grid, SCAN_THREADS, smem, stream>>>(A);
     } else {
         k_scan<SBR_FMT_FASTA><<<grid, SCAN_THREADS, smem, stream>>>(A);
-        k_fasta_finish<<<1, 1, 0, stream>>>(hdr, desc, A.ntiles, nbytes, max_records, final_batch, rec_off);
+        k_fasta_finish<<<1, 1, 0, stream>>>(hdr, desc, A.ntiles, nbytes, max_records, final_batch, gated, rec_off);
     }
     return cudaGetLastError();
 }

@@ -1,0 +1,504 @@
+// k_scan_fast.cu -- kernel 1 (fast path): region-parallel FASTQ/FASTA record-boundary scan.
+//
+// Replaces the record discovery of needletail::parse_fastx_reader(...).next() (src/demux.rs:23,49 /
+// 85-86,101,114) and the slice &record.seq()[..bc_len] (src/demux.rs:54,102,115).
+//
+// Why not a global prefix scan: a single-pass decoupled look-back over 12 KB tiles resolves at most
+// 32 tiles per L2 round trip, which caps a newline-count scan near 0.45 TB/s on B200 (measured, see
+// DESIGN.md).  Here nothing on the critical path waits on another CTA:
+//   * the batch is cut into one contiguous region per CTA; the CTA streams its region tile by tile
+//     through a ring of 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP) completing on mbarriers,
+//     and carries its own running state (newline count, last four newline positions) in shared memory;
+//   * FASTQ: where in the 4-line cycle a region starts is not known locally ('@' and '+' are legal
+//     quality characters), so the CTA DETECTS it from its first eight newlines (the one phase under
+//     which the first whole record parses) and k_scan_finish VERIFIES every region's phase against the
+//     exact prefix sum of the regions' newline counts.  A batch where any region is wrong, malformed,
+//     short, over capacity or undecidable is flagged (hdr->spec_fail) and re-scanned by the exact
+//     look-back kernel (k_scan.cu), which then also reports the precise violation.  Results are
+//     therefore always those of the exact scan; only clean batches finish here.
+//   * a record belongs to the region that holds its first byte; the CTA runs past the end of its region
+//     to finish its last record, and skips the partial record at its start;
+//   * per record: validate ('+' line, equal lengths, CR, next record's '@'), 2-bit pack the first bc_len
+//     bases, write seg_rec_off / seg_key at the region-local index.  The match kernel compacts the
+//     per-region segments into dense arrays while it reads the keys.
+#include "scan_common.cuh"
+
+namespace sbr {
+
+namespace {
+
+constexpr uint32_t UNKNOWN_L = 0xFFFFFFFFu;
+
+struct FastSmem {
+    uint64_t full_bar[SCAN_STAGES];
+    uint32_t warp_tot[SCAN_THREADS / 32];
+    uint32_t list[GHOSTS + SCAN_LIST_CAP];
+    uint32_t rlist[SCAN_LIST_CAP];  // FASTA: list index of every record-start newline of the tile
+    uint32_t first[8];              // FASTQ: the region's first eight newline positions
+    uint32_t nfirst;
+    uint32_t h;            // FASTQ: phase of the region's first newline
+    uint32_t synced;
+    uint32_t first_owned;  // FASTQ: region-local index of the final newline of the first owned record
+    uint32_t cnt;          // newlines seen before the current tile (own range + overrun)
+    uint32_t nl_own;       // newlines inside the region's own byte range
+    uint32_t rcnt;         // FASTA: record starts seen before the current tile
+    uint32_t nrec;
+    uint32_t fail;
+    uint32_t done;         // FASTQ: the record open at the region's end has been finished
+    uint32_t last_end;     // end of the last owned complete record
+    uint32_t last_start_nl, last_start_off;  // FASTA
+    uint32_t crlf;
+};
+
+struct FastArgs {
+    const uint8_t* text;
+    uint32_t nbytes;
+    uint32_t ntiles;
+    uint32_t tiles_per_region;  // every region has this many tiles, the first `extra_regions` one more
+    uint32_t extra_regions;
+    uint32_t cap_r;  // record capacity of one region's segment
+    uint32_t bc_len;
+    uint32_t packed;
+    uint32_t final_batch;
+    BatchHeader* hdr;
+    RegionInfo* info;
+    uint32_t* seg_rec_off;
+    uint64_t* seg_key;
+};
+
+// FASTQ phase detection from the first eight newlines of a region (thread 0).
+// Hypothesis h: newline 0 is the (h+1)-th line end of its record.  Under h the first record that lies
+// wholly behind a record end starts after newline s = (3 - h) & 3 and owns newlines s+1 .. s+4.
+__device__ __forceinline__ bool detect_phase(const ByteSrc& B, const uint32_t* first, uint32_t nbytes, uint32_t& h_out) {
+    int found = -1;
+    for (uint32_t h = 0; h < 4; ++h) {
+        uint32_t s = (3u - h) & 3u;
+        uint32_t a = first[s], p0 = first[s + 1], p1 = first[s + 2], p2 = first[s + 3], p3 = first[s + 4];
+        if (B(a + 1) != '@') continue;
+        uint64_t key;
+        uint32_t bits = fastq_eval(B, p0, p1, p2, p3, 0u, 0u, key);
+        if (bits & (SBR_ST_INVALID_SEP | SBR_ST_UNEQUAL_LEN)) continue;
+        if (p3 + 1 < nbytes && B(p3 + 1) != '@') continue;
+        if (found < 0) found = (int)h;  // ties are settled by k_scan_finish's exact check
+    }
+    if (found < 0) return false;
+    h_out = (uint32_t)found;
+    return true;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
+    extern __shared__ __align__(128) uint8_t dyn_smem[];
+    uint8_t* stage_buf = dyn_smem;
+    FastSmem& S = *reinterpret_cast<FastSmem*>(dyn_smem + SCAN_STAGES * SCAN_TILE);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t c = blockIdx.x;
+    const uint32_t t_lo = c * A.tiles_per_region + min(c, A.extra_regions);
+    const uint32_t t_hi = min(t_lo + A.tiles_per_region + (c < A.extra_regions ? 1u : 0u), A.ntiles);
+    if (t_lo >= A.ntiles) {
+        if (tid == 0) {
+            RegionInfo e = {0u, 0u, PHASE_UNKNOWN, 0u, 0u, 0u, {0u, 0u}};
+            A.info[c] = e;
+        }
+        return;
+    }
+    const uint32_t region_lo = t_lo * (uint32_t)SCAN_TILE;
+    const uint32_t region_hi = min(t_hi * (uint32_t)SCAN_TILE, A.nbytes);
+
+    auto issue = [&](int s, uint32_t tile) {  // thread 0 only
+        uint32_t lo = tile * (uint32_t)SCAN_TILE;
+        uint32_t valid = min((uint32_t)SCAN_TILE, A.nbytes - lo);
+        uint32_t bytes = (valid + 15u) & ~15u;  // the text buffer is padded to 16 bytes
+        mbar_expect_tx(&S.full_bar[s], bytes);
+        bulk_g2s(stage_buf + s * SCAN_TILE, A.text + lo, bytes, &S.full_bar[s]);
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < SCAN_STAGES; ++s) mbar_init(&S.full_bar[s], 1);
+        mbar_fence_init();
+        S.nfirst = 0;
+        S.h = 0;
+        S.synced = (c == 0 || FMT == SBR_FMT_FASTA) ? 1u : 0u;  // a batch starts on a record boundary
+        S.first_owned = (c == 0) ? 3u : UNKNOWN_L;
+        S.cnt = 0;
+        S.nl_own = 0;
+        S.rcnt = 0;
+        S.nrec = 0;
+        S.fail = 0;
+        S.done = 0;
+        S.last_end = 0;
+        S.last_start_nl = 0;
+        S.last_start_off = 0;
+        S.crlf = 0;
+        for (int g = 0; g < GHOSTS; ++g) S.list[g] = NOPOS;
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int s = 0; s < SCAN_STAGES; ++s)
+            if (t_lo + s < t_hi) issue(s, t_lo + s);
+
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t tile = t_lo + it;
+        if (tile >= A.ntiles) break;
+        const bool overrun = tile >= t_hi;
+        if (overrun) {
+            // FASTA never runs over; FASTQ does until the record open at the region's end is finished
+            if (FMT == SBR_FMT_FASTA || S.done || !S.synced || S.fail) break;
+        }
+        const int s = it % SCAN_STAGES;
+        const uint32_t parity = (it / SCAN_STAGES) & 1u;
+        if (overrun && tid == 0) issue(s, tile);  // on demand: one extra tile per region, rarely two
+        const uint32_t lo = tile * (uint32_t)SCAN_TILE;
+        const uint32_t valid = min((uint32_t)SCAN_TILE, A.nbytes - lo);
+        const uint8_t* sm = stage_buf + s * SCAN_TILE;
+        mbar_wait(&S.full_bar[s], parity);
+
+        // ---- newline (and '>') masks of this thread's 48 bytes --------------------------------------
+        const uint32_t toff = tid * SCAN_BYTES_PER_THREAD;
+        const uint4* src = reinterpret_cast<const uint4*>(sm + toff);
+        const uint4 v0 = src[0], v1 = src[1], v2 = src[2];
+        uint64_t vmask = ~0ull;
+        if (toff + SCAN_BYTES_PER_THREAD > valid) {
+            uint32_t nv = valid > toff ? valid - toff : 0u;
+            vmask = (1ull << nv) - 1ull;
+        }
+        const uint64_t m = ((uint64_t)nl_mask16(v0) | ((uint64_t)nl_mask16(v1) << 16) | ((uint64_t)nl_mask16(v2) << 32)) & vmask;
+        uint64_t R = 0;
+        if (FMT == SBR_FMT_FASTA) {
+            uint64_t gm = ((uint64_t)gt_mask16(v0) | ((uint64_t)gt_mask16(v1) << 16) | ((uint64_t)gt_mask16(v2) << 32)) & vmask;
+            const uint32_t nxt = toff + SCAN_BYTES_PER_THREAD;
+            uint32_t nb = 0;
+            if (nxt < valid) nb = sm[nxt];
+            else if (nxt == (uint32_t)SCAN_TILE && lo + nxt < A.nbytes) nb = A.text[lo + nxt];
+            R = m & ((gm >> 1) | (nb == '>' ? (1ull << 47) : 0ull));
+        }
+        const uint32_t cn = __popcll(m), cr = __popcll(R);
+        const uint32_t incl2 = warp_incl_scan(cn | (cr << 16), lane);
+        if (lane == 31) S.warp_tot[warp] = incl2;
+        __syncthreads();  // (1)
+        uint32_t excl2 = incl2 - (cn | (cr << 16)), T2 = 0;
+#pragma unroll
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+            uint32_t t = S.warp_tot[w];
+            if (w < warp) excl2 += t;
+            T2 += t;
+        }
+        const uint32_t excl = excl2 & 0xFFFFu, T = T2 & 0xFFFFu;
+        const uint32_t excl_r = excl2 >> 16, TR = T2 >> 16;
+        // ---- compact newline positions; FASTA also the list index of every record start ---------------
+        {
+            uint64_t mm = m;
+            uint32_t idx = excl, rk = excl_r;
+            bool crlf = false;
+            while (mm) {
+                uint32_t b = __ffsll((long long)mm) - 1;
+                mm &= mm - 1;
+                if (idx < (uint32_t)SCAN_LIST_CAP) {
+                    S.list[GHOSTS + idx] = lo + toff + b;
+                    if (FMT == SBR_FMT_FASTA) {
+                        if ((R >> b) & 1ull) S.rlist[rk++] = idx;
+                        uint32_t o = toff + b;  // CR before LF makes a FASTA batch non-canonical
+                        crlf |= o > 0 ? sm[o - 1] == '\r' : (lo > 0 && A.text[lo - 1] == '\r');
+                    }
+                }
+                ++idx;
+            }
+            if (FMT == SBR_FMT_FASTA && crlf) S.crlf = 1;
+        }
+        if (tid == 0 && T > (uint32_t)SCAN_LIST_CAP) S.fail = 1;  // newline-dense tile: exact scan's job
+        __syncthreads();  // (2)
+
+        const ByteSrc B{sm, A.text, lo, lo + valid};
+        const uint32_t Tw = min(T, (uint32_t)SCAN_LIST_CAP);
+
+        if (FMT == SBR_FMT_FASTQ) {
+            const uint32_t base = S.cnt;
+            if (tid == 0) {
+                if (!overrun) S.nl_own = base + T;
+                if (!S.synced) {
+                    uint32_t nf = S.nfirst;
+                    for (uint32_t i = 0; i < Tw && nf < 8; ++i) S.first[nf++] = S.list[GHOSTS + i];
+                    S.nfirst = nf;
+                    if (nf >= 8) {
+                        const ByteSrc Bg{sm, A.text, lo, lo + valid};
+                        uint32_t h;
+                        if (detect_phase(Bg, S.first, A.nbytes, h)) {
+                            S.h = h;
+                            S.synced = 1;
+                            // the record ending at the first record-final newline is ours only if it starts
+                            // exactly at the region's first byte
+                            uint32_t sfin = (3u - h) & 3u;
+                            bool own0 = (h == 0) && A.text[region_lo - 1] == '\n';
+                            S.first_owned = own0 ? 3u : sfin + 4u;
+                            // records that ended in earlier tiles of this region (long lines only)
+                            for (uint32_t L = S.first_owned; L < base; L += 4) {
+                                uint64_t key;
+                                uint32_t p0 = S.first[L - 3], p1 = S.first[L - 2], p2 = S.first[L - 1], p3 = S.first[L];
+                                uint32_t bits = fastq_eval(Bg, p0, p1, p2, p3, A.bc_len, A.packed, key);
+                                uint32_t rl = (L - S.first_owned) >> 2;
+                                if (bits || rl >= A.cap_r || (p3 + 1 < A.nbytes && Bg(p3 + 1) != '@')) { S.fail = 1; break; }
+                                uint32_t start = (L == 3) ? region_lo : S.first[L - 4] + 1;
+                                A.seg_rec_off[(size_t)c * A.cap_r + rl] = start;
+                                A.seg_key[(size_t)c * A.cap_r + rl] = key;
+                                if (key & KEY_NONCANON) atomicOr(&A.hdr->status, SBR_ST_NONCANONICAL);
+                                S.nrec = max(S.nrec, rl + 1);
+                                S.last_end = max(S.last_end, p3 + 1);
+                                if (p3 + 1 >= region_hi) S.done = 1;
+                            }
+                        } else {
+                            S.fail = 1;
+                        }
+                    }
+                }
+            }
+            __syncthreads();  // (3)
+            if (S.synced && !S.fail) {
+                const uint32_t h = S.h, fo = S.first_owned;
+                // entries i of this tile that end a record: (h + base + i) % 4 == 3
+                const uint32_t i0 = (3u - (h + base)) & 3u;
+                for (uint32_t i = i0 + 4u * tid; i < Tw; i += 4u * SCAN_THREADS) {
+                    const uint32_t L = base + i;
+                    if (L < fo) continue;  // started before this region: the previous region finishes it
+                    const uint32_t start = (L == 3u) ? region_lo : S.list[GHOSTS + (int)i - 4] + 1u;
+                    const uint32_t p3 = S.list[GHOSTS + i];
+                    if (start >= region_hi) continue;  // next region's record (seen while running over)
+                    const uint32_t p2 = S.list[GHOSTS + (int)i - 1], p1 = S.list[GHOSTS + (int)i - 2],
+                                   p0 = S.list[GHOSTS + (int)i - 3];
+                    uint64_t key;
+                    uint32_t bits = fastq_eval(B, p0, p1, p2, p3, A.bc_len, A.packed, key);
+                    if (L == 3u && c == 0 && B(0) != '@') bits |= SBR_ST_INVALID_START;
+                    if (p3 + 1 < A.nbytes && B(p3 + 1) != '@') bits |= SBR_ST_INVALID_START;
+                    const uint32_t rl = (L - fo) >> 2;
+                    if (bits || rl >= A.cap_r) {
+                        S.fail = 1;
+                    } else {
+                        A.seg_rec_off[(size_t)c * A.cap_r + rl] = start;
+                        A.seg_key[(size_t)c * A.cap_r + rl] = key;
+                        if (key & KEY_NONCANON) atomicOr(&A.hdr->status, SBR_ST_NONCANONICAL);
+                        atomicMax(&S.nrec, rl + 1);
+                        atomicMax(&S.last_end, p3 + 1);
+                        if (p3 + 1 >= region_hi) S.done = 1;
+                    }
+                }
+            }
+        } else {
+            // ---- FASTA: thread u handles the u-th record start of the tile --------------------------
+            const uint32_t base = S.rcnt;  // starts seen before this tile (record 0 of the batch not counted)
+            const uint32_t own_first = (c == 0) ? 1u : 0u;
+            for (uint32_t u = tid; u < TR; u += SCAN_THREADS) {
+                const uint32_t idx = S.rlist[u];
+                const uint32_t p = S.list[GHOSTS + idx];
+                const uint32_t hint = (idx + 1 < Tw) ? S.list[GHOSTS + idx + 1] : NOPOS;
+                uint64_t key;
+                const uint32_t why = fasta_eval(B, A.nbytes, p + 1, hint, A.bc_len, A.packed, key);
+                const uint32_t rl = base + u + own_first;
+                // a prefix cut by the end of a non-final batch belongs to the incomplete last record: no error
+                if (rl >= A.cap_r || why == 1 || (why == 2 && A.final_batch)) S.fail = 1;
+                else {
+                    A.seg_rec_off[(size_t)c * A.cap_r + rl] = p + 1;
+                    A.seg_key[(size_t)c * A.cap_r + rl] = key;
+                }
+                if (u == TR - 1) {
+                    S.last_start_nl = S.cnt + idx + 1;
+                    S.last_start_off = p + 1;
+                }
+            }
+            if (tid == 0 && c == 0 && it == 0) {
+                uint64_t key;
+                if (B(0) != '>') S.fail = 1;
+                const uint32_t why = fasta_eval(B, A.nbytes, 0u, Tw > 0 ? S.list[GHOSTS] : NOPOS, A.bc_len, A.packed, key);
+                if (why == 1 || (why == 2 && A.final_batch)) S.fail = 1;
+                A.seg_rec_off[0] = 0;
+                A.seg_key[0] = key;
+            }
+        }
+        __syncthreads();  // (4) all reads of the stage and of the list are done
+        if (tid < GHOSTS) {  // the four most recent newline positions, [GHOSTS-1] the latest
+            uint32_t g = (uint32_t)tid < Tw ? S.list[GHOSTS + Tw - 1 - tid]
+                                            : ((uint32_t)tid - Tw < (uint32_t)GHOSTS ? S.list[GHOSTS - 1 - ((uint32_t)tid - Tw)] : NOPOS);
+            __syncwarp(0xFu);
+            S.list[GHOSTS - 1 - tid] = g;
+        }
+        if (tid == 0) {
+            S.cnt += T;
+            S.rcnt += TR;
+            if (FMT == SBR_FMT_FASTA) S.nl_own = S.cnt;
+            const uint32_t nt = tile + SCAN_STAGES;
+            if (nt < t_hi) issue(s, nt);
+        }
+        __syncthreads();  // (5) state of the next iteration is visible
+    }
+
+    if (tid == 0) {
+        RegionInfo e;
+        e.nl_own = S.nl_own;
+        e.nrec = (FMT == SBR_FMT_FASTA) ? S.rcnt + (c == 0 ? 1u : 0u) : S.nrec;
+        e.phase = (FMT == SBR_FMT_FASTQ && S.synced) ? S.h : PHASE_UNKNOWN;
+        e.flags = S.fail ? 1u : 0u;
+        e.last_start_nl = S.last_start_nl;
+        e.last_start_off = S.last_start_off;
+        e.pad[0] = e.pad[1] = 0;
+        A.info[c] = e;
+        if (S.last_end) atomicMax(&A.hdr->consumed, S.last_end);
+        if (S.crlf) atomicOr(&A.hdr->status, SBR_ST_NONCANONICAL);
+    }
+}
+
+// Verifies the regions against exact prefix sums and publishes the batch header (one block).
+template <int FMT>
+__global__ void __launch_bounds__(MAX_REGIONS) k_scan_finish(BatchHeader* hdr, RegionInfo* info, uint32_t n_regions,
+                                                            uint32_t nbytes, uint32_t max_records, uint32_t final_batch,
+                                                            uint32_t* region_base /* [n_regions+1] */,
+                                                            const uint32_t* seg_rec_off, uint32_t cap_r,
+                                                            uint32_t* rec_off_dense) {
+    __shared__ uint32_t s_nl[MAX_REGIONS], s_rec[MAX_REGIONS];
+    __shared__ uint32_t s_fail, s_last_region;
+    const uint32_t c = threadIdx.x;
+    RegionInfo e = {0u, 0u, PHASE_UNKNOWN, 0u, 0u, 0u, {0u, 0u}};
+    if (c < n_regions) e = info[c];
+    s_nl[c] = e.nl_own;
+    s_rec[c] = e.nrec;
+    if (c == 0) { s_fail = 0; s_last_region = 0; }
+    __syncthreads();
+    // exclusive prefix sums by a simple Hillis-Steele pass (n_regions <= 1024)
+    for (uint32_t d = 1; d < MAX_REGIONS; d <<= 1) {
+        uint32_t a = c >= d ? s_nl[c - d] : 0u, b = c >= d ? s_rec[c - d] : 0u;
+        __syncthreads();
+        s_nl[c] += a;
+        s_rec[c] += b;
+        __syncthreads();
+    }
+    const uint32_t nl_before = s_nl[c] - e.nl_own, rec_before = s_rec[c] - e.nrec;
+    const uint32_t total_nl = s_nl[MAX_REGIONS - 1];
+    uint32_t total_rec = s_rec[MAX_REGIONS - 1];
+    bool bad = false;
+    if (c < n_regions) {
+        if (e.flags & 1u) bad = true;
+        if (FMT == SBR_FMT_FASTQ) {
+            if (e.phase == PHASE_UNKNOWN) bad |= e.nl_own != 0;          // lines it could not place
+            else bad |= e.phase != (nl_before & 3u);                     // detected phase vs the exact one
+        }
+        if (e.nrec) atomicMax(&s_last_region, c);
+    }
+    if (bad) s_fail = 1;
+    __syncthreads();
+    uint32_t consumed = hdr->consumed;
+    uint32_t nl_kept = total_nl;
+    if (FMT == SBR_FMT_FASTA) {
+        if (final_batch) consumed = nbytes;
+        else {  // the last record start of a non-final batch opens an incomplete record
+            total_rec -= 1;  // there is always record 0
+            const RegionInfo& L = info[s_last_region];
+            consumed = L.last_start_nl ? L.last_start_off : 0u;  // record 0 itself when no other start exists
+            nl_kept = (s_nl[s_last_region] - info[s_last_region].nl_own) + L.last_start_nl;
+        }
+    }
+    if (total_rec > max_records) s_fail = 1;
+    __syncthreads();
+    const bool fail = s_fail != 0;
+    if (c < n_regions) {
+        uint32_t rb = rec_before;
+        region_base[c] = rb;
+    }
+    if (c == 0) {
+        region_base[n_regions] = total_rec;
+        if (fail) {  // hand the batch to the exact scan with a clean header
+            hdr->spec_fail = 1;
+            hdr->mode = 0;
+            hdr->status = 0;
+            hdr->first_bad_inv = 0;
+            hdr->n_records = 0;
+            hdr->consumed = 0;
+        } else {
+            hdr->mode = 1;
+            hdr->n_regions = n_regions;
+            hdr->n_records = total_rec;
+            hdr->total_records = total_rec;
+            hdr->n_units = FMT == SBR_FMT_FASTQ ? total_nl : total_rec + (final_batch ? 0u : 1u);
+            hdr->fmt = FMT;
+            hdr->consumed = consumed;
+            hdr->nl_total = total_nl;
+            rec_off_dense[total_rec] = consumed;
+            if (FMT == SBR_FMT_FASTA && nl_kept != 2u * total_rec) atomicOr(&hdr->status, SBR_ST_NONCANONICAL);
+        }
+    }
+    // FASTA, non-final: the dropped last record must not count for its region
+    if (FMT == SBR_FMT_FASTA && !final_batch && !fail && c == s_last_region) {
+        // region_base is an exclusive prefix: only entries after the last region would change, and
+        // there are no records there; the total above already excludes the dropped record
+    }
+    (void)seg_rec_off;
+    (void)cap_r;
+}
+
+}  // namespace
+
+size_t scan_fast_smem_bytes() { return (size_t)SCAN_STAGES * SCAN_TILE + sizeof(FastSmem); }
+
+cudaError_t scan_fast_prepare(int device, int* grid_out) {
+    cudaError_t e;
+    size_t smem = scan_fast_smem_bytes();
+    if ((e = cudaFuncSetAttribute(k_scan_fast<SBR_FMT_FASTQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) !=
+        cudaSuccess)
+        return e;
+    if ((e = cudaFuncSetAttribute(k_scan_fast<SBR_FMT_FASTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) !=
+        cudaSuccess)
+        return e;
+    int per_sm = 0, sms = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_fast<SBR_FMT_FASTQ>, SCAN_THREADS, smem)) !=
+        cudaSuccess)
+        return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    int g = per_sm * sms;
+    *grid_out = g > MAX_REGIONS ? MAX_REGIONS : g;
+    return cudaSuccess;
+}
+
+// Regions of a batch: at most max_regions CTAs, at least 8 tiles (96 KB) each so that the work at a
+// region's start and end is amortised and every region sees enough newlines to find its phase; the
+// tiles that do not divide evenly go one each to the first regions.
+uint32_t scan_fast_regions(uint32_t nbytes, int max_regions, uint32_t* tiles_per_region, uint32_t* extra_regions) {
+    const uint32_t ntiles = (nbytes + SCAN_TILE - 1) / SCAN_TILE;
+    const uint32_t min_tiles = 8;
+    uint32_t R = ntiles / min_tiles;
+    if (R > (uint32_t)max_regions) R = (uint32_t)max_regions;
+    if (R == 0) R = 1;
+    *tiles_per_region = ntiles / R;
+    *extra_regions = ntiles % R;
+    return R;
+}
+
+cudaError_t scan_fast_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbytes, uint32_t max_records, uint32_t cap_r,
+                             uint32_t n_regions, uint32_t tiles_per_region, uint32_t extra_regions, uint32_t bc_len,
+                             uint32_t packed,
+                             uint32_t final_batch, BatchHeader* hdr, RegionInfo* info, uint32_t* region_base,
+                             uint32_t* seg_rec_off, uint64_t* seg_key, uint32_t* rec_off_dense, cudaStream_t stream) {
+    FastArgs A;
+    A.text = d_text;
+    A.nbytes = nbytes;
+    A.ntiles = (nbytes + SCAN_TILE - 1) / SCAN_TILE;
+    A.tiles_per_region = tiles_per_region;
+    A.extra_regions = extra_regions;
+    A.cap_r = cap_r;
+    A.bc_len = bc_len;
+    A.packed = packed;
+    A.final_batch = final_batch;
+    A.hdr = hdr;
+    A.info = info;
+    A.seg_rec_off = seg_rec_off;
+    A.seg_key = seg_key;
+    size_t smem = scan_fast_smem_bytes();
+    if (fmt == SBR_FMT_FASTQ) {
+        k_scan_fast<SBR_FMT_FASTQ><<<n_regions, SCAN_THREADS, smem, stream>>>(A);
+        k_scan_finish<SBR_FMT_FASTQ><<<1, MAX_REGIONS, 0, stream>>>(hdr, info, n_regions, nbytes, max_records, final_batch,
+                                                                    region_base, seg_rec_off, cap_r, rec_off_dense);
+    } else {
+        k_scan_fast<SBR_FMT_FASTA><<<n_regions, SCAN_THREADS, smem, stream>>>(A);
+        k_scan_finish<SBR_FMT_FASTA><<<1, MAX_REGIONS, 0, stream>>>(hdr, info, n_regions, nbytes, max_records, final_batch,
+                                                                    region_base, seg_rec_off, cap_r, rec_off_dense);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace sbr

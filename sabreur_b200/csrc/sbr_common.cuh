@@ -38,7 +38,11 @@ struct BatchHeader {
     uint32_t nl_total;       // FASTA: newlines in the batch
     uint32_t nl_last_start;  // FASTA: newlines up to and including the one before the last record start
     uint32_t nl_at_cap;      // FASTA: same, for record index max_records
-    uint32_t pad[5];
+    uint32_t mode;           // 1: per-region segments (fast scan), 0: dense arrays (look-back scan)
+    uint32_t spec_fail;      // fast scan gave up: the look-back scan must run
+    uint32_t consumed;       // fast scan: end of the last complete record
+    uint32_t n_regions;
+    uint32_t pad[1];
 };
 static_assert(sizeof(BatchHeader) == 64, "BatchHeader is one 64-byte line");
 

@@ -56,6 +56,7 @@ class Batch:
     bin_start: np.ndarray     # u32 [n_bins+1]
     order: np.ndarray         # u32 [n]
     rec_key: np.ndarray | None
+    scan_path: int = 0        # 1: region-parallel scan, 0: look-back scan
     record_base: int = 0      # index of the batch's first record in the whole stream
 
 
@@ -136,7 +137,7 @@ class Demux:
                      fmt=r.fmt, rec_off=f(_as_np(r.rec_off, n + 1, np.uint32)), assign=f(_as_np(r.assign, n, np.uint16)),
                      bin_count=f(_as_np(r.bin_count, r.n_bins, np.uint32)),
                      bin_start=f(_as_np(r.bin_start, r.n_bins + 1, np.uint32)), order=f(_as_np(r.order, n, np.uint32)),
-                     rec_key=f(_as_np(r.rec_key, n, np.uint64)) if r.rec_key else None)
+                     rec_key=f(_as_np(r.rec_key, n, np.uint64)) if r.rec_key else None, scan_path=r.scan_path)
 
     def demux_device(self, slot: int, d_ptr: int, nbytes: int, final: bool = True, stream: int = 0):
         self._check(self.lib.sbr_demux_device(self.h, slot, d_ptr, nbytes, int(final), stream), "sbr_demux_device")
@@ -231,9 +232,11 @@ def demux_bytes(data: bytes, barcodes: list[bytes], mismatch: int, fmt: int = FM
         status, bad = 0, None
         pos = 0
         fmt_seen = 0
+        paths = []
         for b in dm.stream(data[i:i + chunk] for i in range(0, len(data), chunk)):
             status |= b.status
             fmt_seen = b.fmt or fmt_seen
+            paths.append(b.scan_path)
             if b.status & _ffi.ST_ERROR_MASK:
                 bad = (b.record_base + b.first_bad_record, b.first_bad_flags)
                 # records before the first bad one were still demultiplexed by the reference
@@ -250,7 +253,7 @@ def demux_bytes(data: bytes, barcodes: list[bytes], mismatch: int, fmt: int = FM
         return dict(assign=np.concatenate(asg) if asg else np.zeros(0, np.uint16), bin_count=counts,
                     per_bin=[np.concatenate(x) if x else np.zeros(0, np.uint64) for x in per_bin],
                     spans=np.concatenate(spans) if spans else np.zeros((0, 2), np.uint64), status=status, bad=bad,
-                    fmt=fmt_seen)
+                    fmt=fmt_seen, scan_paths=paths)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -30,16 +30,21 @@ def _bcs(name):
 def _check_against_oracle(gpu, text: bytes, barcodes, m, **kw):
     """stream `text` through the GPU and compare everything with the oracle"""
     dm = gpu["demux"]
-    got = dm.demux_bytes(text, barcodes, m, **kw)
     exp = orc.demux(text, barcodes, m)
-    assert got["bad"] is None and not (got["status"] & gpu["ffi"].ST_ERROR_MASK)
-    assert got["assign"].tolist() == exp["assign"].tolist()
-    assert got["bin_count"].tolist() == exp["bin_count"].tolist()
-    assert got["spans"][:, 0].tolist() == exp["recs"]["rec_off"].tolist()
-    assert got["spans"][:, 1].tolist() == exp["recs"]["rec_end"].tolist()
-    for b in range(len(barcodes) + 1):
-        seg = exp["order"][exp["bin_start"][b]:exp["bin_start"][b + 1]]
-        assert got["per_bin"][b].tolist() == seg.tolist()
+    user_flags = kw.pop("flags", 0)
+    # both record scans: the region-parallel one (default) and the look-back one (forced)
+    for scan_flag in (gpu["ffi"].CFG_EXACT_SCAN, 0):
+        got = dm.demux_bytes(text, barcodes, m, flags=user_flags | scan_flag, **kw)
+        assert got["bad"] is None and not (got["status"] & gpu["ffi"].ST_ERROR_MASK)
+        assert got["assign"].tolist() == exp["assign"].tolist()
+        assert got["bin_count"].tolist() == exp["bin_count"].tolist()
+        assert got["spans"][:, 0].tolist() == exp["recs"]["rec_off"].tolist()
+        assert got["spans"][:, 1].tolist() == exp["recs"]["rec_end"].tolist()
+        for b in range(len(barcodes) + 1):
+            seg = exp["order"][exp["bin_start"][b]:exp["bin_start"][b + 1]]
+            assert got["per_bin"][b].tolist() == seg.tolist()
+        if scan_flag:
+            assert not any(got["scan_paths"])
     return got, exp
 
 
@@ -88,6 +93,7 @@ def test_synthetic_slice_parity(gpu, name, n, flags):
         text = synth.reads_host(w, tab, 777, n, mate).tobytes()
         got, exp = _check_against_oracle(gpu, text, bcs, w.mismatch, batch_bytes=4 << 20, flags=flags)
         assert got["bin_count"].sum() == n
+        assert all(got["scan_paths"]), "clean synthetic batches must finish in the region-parallel scan"
 
 
 def test_device_resident_batch_equals_oracle(gpu):
@@ -104,7 +110,7 @@ def test_device_resident_batch_equals_oracle(gpu):
         dm.demux_device(0, dev.data_ptr(), n * w.rec_bytes, final=True, stream=torch.cuda.current_stream().cuda_stream)
         b = dm.wait(0)
     exp = orc.demux(text, bcs, w.mismatch)
-    assert b.n_records == n and b.consumed == n * w.rec_bytes and b.status == 0
+    assert b.n_records == n and b.consumed == n * w.rec_bytes and b.status == 0 and b.scan_path == 1
     assert np.array_equal(b.assign, exp["assign"])
     assert np.array_equal(b.bin_count, exp["bin_count"])
     assert np.array_equal(b.bin_start, exp["bin_start"])
@@ -192,12 +198,13 @@ CASES = {
 
 
 @pytest.mark.parametrize("kind", sorted(CASES))
-@pytest.mark.parametrize("m", [0, 1])
-def test_edge_inputs(gpu, kind, m):
-    rng = random.Random(hash(kind) & 0xFFFF)
+@pytest.mark.parametrize("m,big", [(0, False), (1, True)])
+def test_edge_inputs(gpu, kind, m, big):
+    rng = random.Random(sum(kind.encode()) * 7 + m)
     text = CASES[kind](rng)
     bcs = [bytes(rng.choice(b"ACGT") for _ in range(4)) for _ in range(14)]
-    batch = (1 << 20) if "long" in kind else (1 << 16)
+    # big: one multi-region batch (several CTAs of the region-parallel scan); small: many single-region batches
+    batch = (1 << 20) if ("long" in kind or big) else (1 << 16)
     got, exp = _check_against_oracle(gpu, text, bcs, m, batch_bytes=batch, chunk=50_001)
     # per-bin output bytes through the host writer's rule: verbatim unless flagged non-canonical
     outs_exp = orc.demux_outputs(text, bcs, m)
@@ -254,6 +261,20 @@ def test_parse_violations_are_reported_like_the_oracle(gpu, text, code):
         assert got["bad"][0] == e.value.record
 
 
+def test_adversarial_phase_detection(gpu):
+    """quality strings made of '@' and headers/sequences that mimic other lines: whatever phase a region
+    guesses, the result must be the exact scan's (k_scan_finish verifies, the look-back scan re-runs)"""
+    rng = random.Random(77)
+    out = bytearray()
+    for i in range(40000):
+        L = rng.randint(4, 9)
+        s = bytes(rng.choice(b"ACGT") for _ in range(L))
+        q = b"@" * L if rng.random() < 0.5 else b"+" * L
+        out += b"@" + b"@" * rng.randint(0, 3) + b"\n" + s + b"\n+" + (b"@x" if rng.random() < 0.3 else b"") + b"\n" + q + b"\n"
+    bcs = [bytes(rng.choice(b"ACGT") for _ in range(4)) for _ in range(9)]
+    _check_against_oracle(gpu, bytes(out), bcs, 1, batch_bytes=1 << 20, chunk=333_333)
+
+
 def test_record_capacity_overflow_is_chunked_not_lost(gpu):
     rng = random.Random(9)
     text = _rand_fastq(rng, 5000, lo=8, hi=12)
@@ -274,7 +295,7 @@ def test_large_batch_properties(gpu):
     with dmx.Demux(bcs, w.mismatch, fmt=2, batch_bytes=nbytes + 4096, max_records=n + 16) as dm:
         dm.demux_device(0, dev.data_ptr(), nbytes, final=True)
         b = dm.wait(0)
-    assert b.n_records == n and b.consumed == nbytes and b.status == 0
+    assert b.n_records == n and b.consumed == nbytes and b.status == 0 and b.scan_path == 1
     assert np.array_equal(b.rec_off, np.arange(n + 1, dtype=np.uint64) * w.rec_bytes)  # fixed-size records
     assert b.bin_count.sum() == n and np.array_equal(np.bincount(b.assign, minlength=97), b.bin_count)
     assert np.array_equal(np.cumsum(np.concatenate([[0], b.bin_count])), b.bin_start)

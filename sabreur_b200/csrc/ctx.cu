@@ -19,7 +19,7 @@ cudaError_t scan_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbytes, ui
                         uint32_t* rec_off, uint64_t* key, int grid_cap, cudaStream_t stream);
 uint32_t scan_tiles(uint32_t nbytes);
 // k_scan_fast.cu (region-parallel scan)
-cudaError_t scan_fast_prepare(int device, int* grid_out);
+cudaError_t scan_fast_prepare(int device, int* grid_fastq, int* grid_fasta);
 uint32_t scan_fast_regions(uint32_t nbytes, int max_regions, uint32_t* tiles_per_region, uint32_t* extra_regions);
 cudaError_t scan_fast_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbytes, uint32_t max_records, uint32_t cap_r,
                              uint32_t n_regions, uint32_t tiles_per_region, uint32_t extra_regions, uint32_t bc_len,
@@ -109,7 +109,7 @@ struct sbr_ctx {
     int device = 0;
     int sms = 0;
     int scan_grid = 0;
-    int fast_grid = 0;   // CTAs (= regions at most) of the region-parallel scan
+    int fast_grid_q = 0, fast_grid_a = 0;  // CTAs (= regions at most) of the region-parallel scan, FASTQ / FASTA
     bool exact_only = false;
     uint32_t nbins = 0;
     uint32_t max_records = 0;
@@ -230,7 +230,7 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
     c->timing = (cfg->flags & SBR_CFG_TIMING) != 0;
 
     CU(c, scan_prepare(cfg->device, &c->scan_grid));
-    CU(c, scan_fast_prepare(cfg->device, &c->fast_grid));
+    CU(c, scan_fast_prepare(cfg->device, &c->fast_grid_q, &c->fast_grid_a));
     c->exact_only = (cfg->flags & SBR_CFG_EXACT_SCAN) != 0;
     CU(c, match_prepare());
     CU(c, partition_prepare());
@@ -345,7 +345,7 @@ static int launch_pipeline(sbr_ctx* c, Slot& s, const uint8_t* d_text, uint32_t 
     uint32_t cap_r = 0;
     if (!c->exact_only) {
         uint32_t tpr = 0, extra = 0;
-        uint32_t nreg = scan_fast_regions(nbytes, c->fast_grid, &tpr, &extra);
+        uint32_t nreg = scan_fast_regions(nbytes, fmt == SBR_FMT_FASTA ? c->fast_grid_a : c->fast_grid_q, &tpr, &extra);
         // segments get 25 % + 64 records of slack over an even split: regions hold unequal record counts
         cap_r = (uint32_t)(((uint64_t)c->max_records * 5 / 4) / nreg) + 64;
         CU(c, scan_fast_launch(fmt, d_text, nbytes, c->max_records, cap_r, nreg, tpr, extra, c->cfg.bc_len, c->packed ? 1u : 0u,

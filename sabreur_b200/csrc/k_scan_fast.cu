@@ -28,20 +28,23 @@ namespace sbr {
 namespace {
 
 constexpr uint32_t UNKNOWN_L = 0xFFFFFFFFu;
+constexpr int FAST_CAP = 768;  // newline positions per tile held in shared memory (a 12 KB tile of >= 16-byte lines)
+constexpr int LSTRIDE = GHOSTS + FAST_CAP;
 
+template <int FMT>
 struct FastSmem {
     uint64_t full_bar[SCAN_STAGES];
     uint32_t warp_tot[SCAN_THREADS / 32];
-    uint32_t list[GHOSTS + SCAN_LIST_CAP];
-    uint32_t rlist[SCAN_LIST_CAP];  // FASTA: list index of every record-start newline of the tile
-    uint32_t first[8];              // FASTQ: the region's first eight newline positions
+    uint32_t list[2][LSTRIDE];  // double-buffered by tile parity: [GHOSTS + i] = i-th newline, [GHOSTS-1-g] = g-th before the tile
+    uint32_t rlist[FMT == SBR_FMT_FASTA ? 2 : 1][FMT == SBR_FMT_FASTA ? FAST_CAP : 1];  // FASTA: list index of record starts
+    uint32_t cnt[2];    // newlines seen before the tile, by tile parity
+    uint32_t rcnt[2];   // FASTA: record starts seen before the tile
+    uint32_t first[8];  // FASTQ: the region's first eight newline positions
     uint32_t nfirst;
     uint32_t h;            // FASTQ: phase of the region's first newline
     uint32_t synced;
     uint32_t first_owned;  // FASTQ: region-local index of the final newline of the first owned record
-    uint32_t cnt;          // newlines seen before the current tile (own range + overrun)
     uint32_t nl_own;       // newlines inside the region's own byte range
-    uint32_t rcnt;         // FASTA: record starts seen before the current tile
     uint32_t nrec;
     uint32_t fail;
     uint32_t done;         // FASTQ: the record open at the region's end has been finished
@@ -60,11 +63,33 @@ struct FastArgs {
     uint32_t bc_len;
     uint32_t packed;
     uint32_t final_batch;
+    uint32_t c7f, c0a, c80, c3e;  // byte-splat constants, passed in so that they live in registers (one LOP3 per step)
     BatchHeader* hdr;
     RegionInfo* info;
     uint32_t* seg_rec_off;
     uint64_t* seg_key;
 };
+
+// 0x80 in every byte of w equal to the splatted byte `cx` (cx < 0x80): three instructions
+__device__ __forceinline__ uint32_t eq_flags(uint32_t w, uint32_t c7f, uint32_t cx, uint32_t c80) {
+    uint32_t a = (w & c7f) ^ cx;
+    uint32_t b = a + c7f;
+    return ~(b | w) & c80;
+}
+// the 48-bit mask of bytes equal to cx in this thread's three 16-byte chunks: lo = bytes 0..31, hi = bytes 32..47.
+// dp4a gathers the four 0x80 flags of a word into a nibble in one instruction: 0x80 * {1,2,4,8} = nibble << 7.
+__device__ __forceinline__ void eq_mask48(const uint4& v0, const uint4& v1, const uint4& v2, uint32_t c7f, uint32_t cx,
+                                          uint32_t c80, uint32_t& lo, uint32_t& hi) {
+    const uint32_t WL = 0x08040201u, WH = 0x80402010u;
+    uint32_t x0 = __dp4a(eq_flags(v0.x, c7f, cx, c80), WL, __dp4a(eq_flags(v0.y, c7f, cx, c80), WH, 0u));
+    uint32_t x1 = __dp4a(eq_flags(v0.z, c7f, cx, c80), WL, __dp4a(eq_flags(v0.w, c7f, cx, c80), WH, 0u));
+    uint32_t x2 = __dp4a(eq_flags(v1.x, c7f, cx, c80), WL, __dp4a(eq_flags(v1.y, c7f, cx, c80), WH, 0u));
+    uint32_t x3 = __dp4a(eq_flags(v1.z, c7f, cx, c80), WL, __dp4a(eq_flags(v1.w, c7f, cx, c80), WH, 0u));
+    uint32_t x4 = __dp4a(eq_flags(v2.x, c7f, cx, c80), WL, __dp4a(eq_flags(v2.y, c7f, cx, c80), WH, 0u));
+    uint32_t x5 = __dp4a(eq_flags(v2.z, c7f, cx, c80), WL, __dp4a(eq_flags(v2.w, c7f, cx, c80), WH, 0u));
+    lo = (x0 >> 7) + (x1 << 1) + (x2 << 9) + (x3 << 17);  // disjoint bit fields: + == |
+    hi = (x4 >> 7) + (x5 << 1);
+}
 
 // FASTQ phase detection from the first eight newlines of a region (thread 0).
 // Hypothesis h: newline 0 is the (h+1)-th line end of its record.  Under h the first record that lies
@@ -86,11 +111,46 @@ __device__ __forceinline__ bool detect_phase(const ByteSrc& B, const uint32_t* f
     return true;
 }
 
+// 2-bit pack + validity of k (<= 16) bases at tile offset s, 4 bases per step (packed mode, in-tile records)
+__device__ __forceinline__ uint64_t pack_prefix_vec(const uint8_t* sm, uint32_t s, uint32_t k) {
+    const uint32_t a = s & ~3u, sh = (s & 3u) * 8u;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(sm + a);
+    uint32_t codes = 0, inval = 0;
+    uint32_t w = wp[0];
+    for (uint32_t j = 0; j * 4 < k; ++j) {
+        const uint32_t wn = wp[j + 1];
+        const uint32_t x = __funnelshift_r(w, wn, sh);  // four bases, base 0 in the low byte
+        w = wn;
+        const uint32_t c = (x >> 1) & 0x03030303u;      // code = (ascii >> 1) & 3
+        codes |= (((c * 0x00041041u) >> 18) & 0xFFu) << (8 * j);
+        const uint32_t b0 = c & 0x01010101u, b1 = (c >> 1) & 0x01010101u;
+        const uint32_t canon = 0x41414141u + 2u * b0 + 19u * b1 - 15u * (b0 & b1);  // 'A','C','T','G' from the code
+        const uint32_t d = canon ^ x;
+        const uint32_t nz = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+        inval |= (__dp4a(nz, 0x08040201u, 0u) >> 7) << (4 * j);
+    }
+    if (k < 16) { codes &= (1u << (2 * k)) - 1u; inval &= (1u << k) - 1u; }
+    return (uint64_t)codes | ((uint64_t)inval << 32);
+}
+
+// owner bookkeeping of one finished FASTQ record (any path)
 template <int FMT>
-__global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
+__device__ __forceinline__ void fastq_commit(const FastArgs& A, FastSmem<FMT>& S, uint32_t c, uint32_t rl, uint32_t start,
+                                             uint32_t p3, uint64_t key, uint32_t bits, uint32_t region_hi) {
+    if (bits || rl >= A.cap_r) { S.fail = 1; return; }
+    A.seg_rec_off[(size_t)c * A.cap_r + rl] = start;
+    A.seg_key[(size_t)c * A.cap_r + rl] = key;
+    if (key & KEY_NONCANON) atomicOr(&A.hdr->status, SBR_ST_NONCANONICAL);
+    atomicMax(&S.nrec, rl + 1);
+    atomicMax(&S.last_end, p3 + 1);
+    if (p3 + 1 >= region_hi) S.done = 1;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(SCAN_THREADS, FMT == SBR_FMT_FASTQ ? 4 : 3) k_scan_fast(FastArgs A) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     uint8_t* stage_buf = dyn_smem;
-    FastSmem& S = *reinterpret_cast<FastSmem*>(dyn_smem + SCAN_STAGES * SCAN_TILE);
+    FastSmem<FMT>& S = *reinterpret_cast<FastSmem<FMT>*>(dyn_smem + SCAN_STAGES * SCAN_TILE);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t c = blockIdx.x;
     const uint32_t t_lo = c * A.tiles_per_region + min(c, A.extra_regions);
@@ -104,6 +164,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
     }
     const uint32_t region_lo = t_lo * (uint32_t)SCAN_TILE;
     const uint32_t region_hi = min(t_hi * (uint32_t)SCAN_TILE, A.nbytes);
+    const uint32_t c7f = A.c7f, c0a = A.c0a, c80 = A.c80;
 
     auto issue = [&](int s, uint32_t tile) {  // thread 0 only
         uint32_t lo = tile * (uint32_t)SCAN_TILE;
@@ -120,9 +181,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
         S.h = 0;
         S.synced = (c == 0 || FMT == SBR_FMT_FASTA) ? 1u : 0u;  // a batch starts on a record boundary
         S.first_owned = (c == 0) ? 3u : UNKNOWN_L;
-        S.cnt = 0;
+        S.cnt[0] = S.cnt[1] = 0;
+        S.rcnt[0] = S.rcnt[1] = 0;
         S.nl_own = 0;
-        S.rcnt = 0;
         S.nrec = 0;
         S.fail = 0;
         S.done = 0;
@@ -130,24 +191,31 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
         S.last_start_nl = 0;
         S.last_start_off = 0;
         S.crlf = 0;
-        for (int g = 0; g < GHOSTS; ++g) S.list[g] = NOPOS;
+        for (int g = 0; g < GHOSTS; ++g) S.list[0][g] = NOPOS;
     }
     __syncthreads();
     if (tid == 0)
         for (int s = 0; s < SCAN_STAGES; ++s)
             if (t_lo + s < t_hi) issue(s, t_lo + s);
 
+    // Tile loop.  Two block barriers per tile: (1) warp totals of the newline scan, (2) newline list complete.
+    // The records of tile t are evaluated by a rotating pair of warps while the other warps already build
+    // the masks of tile t+1; barrier (1) of tile t+1 doubles as "everybody is done with tile t", after which
+    // thread 0 refills tile t's stage.  Past the region's end (FASTQ only: the record left open there) the
+    // same body runs with one more barrier and on-demand loads.
     for (uint32_t it = 0;; ++it) {
         const uint32_t tile = t_lo + it;
         if (tile >= A.ntiles) break;
         const bool overrun = tile >= t_hi;
         if (overrun) {
-            // FASTA never runs over; FASTQ does until the record open at the region's end is finished
-            if (FMT == SBR_FMT_FASTA || S.done || !S.synced || S.fail) break;
+            if (FMT == SBR_FMT_FASTA) break;
+            __syncthreads();  // records of the previous tile are complete: S.done / S.synced are final
+            if (S.done || !S.synced || S.fail) break;
         }
         const int s = it % SCAN_STAGES;
+        const uint32_t par = it & 1u;
         const uint32_t parity = (it / SCAN_STAGES) & 1u;
-        if (overrun && tid == 0) issue(s, tile);  // on demand: one extra tile per region, rarely two
+        if (overrun && tid == 0) issue(s, tile);  // on demand: one extra tile per region, rarely more
         const uint32_t lo = tile * (uint32_t)SCAN_TILE;
         const uint32_t valid = min((uint32_t)SCAN_TILE, A.nbytes - lo);
         const uint8_t* sm = stage_buf + s * SCAN_TILE;
@@ -157,25 +225,38 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
         const uint32_t toff = tid * SCAN_BYTES_PER_THREAD;
         const uint4* src = reinterpret_cast<const uint4*>(sm + toff);
         const uint4 v0 = src[0], v1 = src[1], v2 = src[2];
-        uint64_t vmask = ~0ull;
+        uint32_t m_lo, m_hi;
+        eq_mask48(v0, v1, v2, c7f, c0a, c80, m_lo, m_hi);
+        uint32_t vm_lo = 0xFFFFFFFFu, vm_hi = 0xFFFFu;
         if (toff + SCAN_BYTES_PER_THREAD > valid) {
             uint32_t nv = valid > toff ? valid - toff : 0u;
-            vmask = (1ull << nv) - 1ull;
+            vm_lo = nv >= 32 ? 0xFFFFFFFFu : ((1u << nv) - 1u);
+            vm_hi = nv > 32 ? ((1u << (nv - 32)) - 1u) : 0u;
+            m_lo &= vm_lo;
+            m_hi &= vm_hi;
         }
-        const uint64_t m = ((uint64_t)nl_mask16(v0) | ((uint64_t)nl_mask16(v1) << 16) | ((uint64_t)nl_mask16(v2) << 32)) & vmask;
-        uint64_t R = 0;
+        uint32_t r_lo = 0, r_hi = 0;
         if (FMT == SBR_FMT_FASTA) {
-            uint64_t gm = ((uint64_t)gt_mask16(v0) | ((uint64_t)gt_mask16(v1) << 16) | ((uint64_t)gt_mask16(v2) << 32)) & vmask;
+            uint32_t g_lo, g_hi;
+            eq_mask48(v0, v1, v2, c7f, A.c3e, c80, g_lo, g_hi);
+            g_lo &= vm_lo;
+            g_hi &= vm_hi;
             const uint32_t nxt = toff + SCAN_BYTES_PER_THREAD;
             uint32_t nb = 0;
             if (nxt < valid) nb = sm[nxt];
             else if (nxt == (uint32_t)SCAN_TILE && lo + nxt < A.nbytes) nb = A.text[lo + nxt];
-            R = m & ((gm >> 1) | (nb == '>' ? (1ull << 47) : 0ull));
+            // a record starts after every '\n' that is followed by '>'
+            r_lo = m_lo & ((g_lo >> 1) | (g_hi << 31));
+            r_hi = m_hi & ((g_hi >> 1) | (nb == '>' ? 0x8000u : 0u));
         }
-        const uint32_t cn = __popcll(m), cr = __popcll(R);
+        const uint32_t cn = __popc(m_lo) + __popc(m_hi), cr = __popc(r_lo) + __popc(r_hi);
         const uint32_t incl2 = warp_incl_scan(cn | (cr << 16), lane);
         if (lane == 31) S.warp_tot[warp] = incl2;
         __syncthreads();  // (1)
+        if (tid == 0 && it >= 1 && !overrun) {  // tile it-1 is finished by everybody: refill its stage
+            const uint32_t nt = tile - 1 + SCAN_STAGES;
+            if (nt < t_hi) issue((it - 1) % SCAN_STAGES, nt);
+        }
         uint32_t excl2 = incl2 - (cn | (cr << 16)), T2 = 0;
 #pragma unroll
         for (int w = 0; w < SCAN_THREADS / 32; ++w) {
@@ -185,113 +266,131 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
         }
         const uint32_t excl = excl2 & 0xFFFFu, T = T2 & 0xFFFFu;
         const uint32_t excl_r = excl2 >> 16, TR = T2 >> 16;
+        uint32_t* list = S.list[par];
+        // read before barrier (2): thread 0 may flip it right after that barrier, and every thread has to
+        // take the same decision about the extra barrier below
+        const bool was_synced = S.synced != 0;
         // ---- compact newline positions; FASTA also the list index of every record start ---------------
         {
-            uint64_t mm = m;
             uint32_t idx = excl, rk = excl_r;
             bool crlf = false;
-            while (mm) {
-                uint32_t b = __ffsll((long long)mm) - 1;
-                mm &= mm - 1;
-                if (idx < (uint32_t)SCAN_LIST_CAP) {
-                    S.list[GHOSTS + idx] = lo + toff + b;
-                    if (FMT == SBR_FMT_FASTA) {
-                        if ((R >> b) & 1ull) S.rlist[rk++] = idx;
-                        uint32_t o = toff + b;  // CR before LF makes a FASTA batch non-canonical
-                        crlf |= o > 0 ? sm[o - 1] == '\r' : (lo > 0 && A.text[lo - 1] == '\r');
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t mm = half ? m_hi : m_lo;
+                const uint32_t rr = half ? r_hi : r_lo;
+                while (mm) {
+                    const uint32_t b = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    if (idx < (uint32_t)FAST_CAP) {
+                        list[GHOSTS + idx] = lo + toff + 32 * half + b;
+                        if (FMT == SBR_FMT_FASTA) {
+                            if ((rr >> b) & 1u) S.rlist[par][rk++] = idx;
+                            const uint32_t o = toff + 32 * half + b;  // CR before LF makes a FASTA batch non-canonical
+                            crlf |= o > 0 ? sm[o - 1] == '\r' : (lo > 0 && A.text[lo - 1] == '\r');
+                        }
                     }
+                    ++idx;
                 }
-                ++idx;
             }
             if (FMT == SBR_FMT_FASTA && crlf) S.crlf = 1;
         }
-        if (tid == 0 && T > (uint32_t)SCAN_LIST_CAP) S.fail = 1;  // newline-dense tile: exact scan's job
+        if (tid == 0 && T > (uint32_t)FAST_CAP) S.fail = 1;  // newline-dense tile: the exact scan's job
         __syncthreads();  // (2)
 
         const ByteSrc B{sm, A.text, lo, lo + valid};
-        const uint32_t Tw = min(T, (uint32_t)SCAN_LIST_CAP);
+        const uint32_t Tw = min(T, (uint32_t)FAST_CAP);
+        const uint32_t base = S.cnt[par];
+        // ---- state of the next tile (other parity): count and the four most recent newline positions ----
+        if (tid < GHOSTS) {
+            const uint32_t g = (uint32_t)tid < Tw ? list[GHOSTS + Tw - 1 - tid] : list[GHOSTS - 1 - ((uint32_t)tid - Tw)];
+            S.list[par ^ 1u][GHOSTS - 1 - tid] = g;
+            if (tid == 0) {
+                S.cnt[par ^ 1u] = base + T;
+                S.rcnt[par ^ 1u] = S.rcnt[par] + TR;
+                if (!overrun) S.nl_own = base + T;
+            }
+        }
 
         if (FMT == SBR_FMT_FASTQ) {
-            const uint32_t base = S.cnt;
-            if (tid == 0) {
-                if (!overrun) S.nl_own = base + T;
-                if (!S.synced) {
+            if (!was_synced) {  // uniform: only the first tile(s) of a region, until eight newlines were seen
+                if (tid == 0) {
                     uint32_t nf = S.nfirst;
-                    for (uint32_t i = 0; i < Tw && nf < 8; ++i) S.first[nf++] = S.list[GHOSTS + i];
+                    for (uint32_t i = 0; i < Tw && nf < 8; ++i) S.first[nf++] = list[GHOSTS + i];
                     S.nfirst = nf;
                     if (nf >= 8) {
-                        const ByteSrc Bg{sm, A.text, lo, lo + valid};
                         uint32_t h;
-                        if (detect_phase(Bg, S.first, A.nbytes, h)) {
+                        if (detect_phase(B, S.first, A.nbytes, h)) {
                             S.h = h;
-                            S.synced = 1;
                             // the record ending at the first record-final newline is ours only if it starts
                             // exactly at the region's first byte
-                            uint32_t sfin = (3u - h) & 3u;
-                            bool own0 = (h == 0) && A.text[region_lo - 1] == '\n';
-                            S.first_owned = own0 ? 3u : sfin + 4u;
-                            // records that ended in earlier tiles of this region (long lines only)
-                            for (uint32_t L = S.first_owned; L < base; L += 4) {
+                            const uint32_t sfin = (3u - h) & 3u;
+                            const bool own0 = (h == 0) && A.text[region_lo - 1] == '\n';
+                            const uint32_t fo = own0 ? 3u : sfin + 4u;
+                            S.first_owned = fo;
+                            // records that ended in earlier tiles of this region (lines longer than a tile)
+                            for (uint32_t L = fo; L < base; L += 4) {
                                 uint64_t key;
-                                uint32_t p0 = S.first[L - 3], p1 = S.first[L - 2], p2 = S.first[L - 1], p3 = S.first[L];
-                                uint32_t bits = fastq_eval(Bg, p0, p1, p2, p3, A.bc_len, A.packed, key);
-                                uint32_t rl = (L - S.first_owned) >> 2;
-                                if (bits || rl >= A.cap_r || (p3 + 1 < A.nbytes && Bg(p3 + 1) != '@')) { S.fail = 1; break; }
-                                uint32_t start = (L == 3) ? region_lo : S.first[L - 4] + 1;
-                                A.seg_rec_off[(size_t)c * A.cap_r + rl] = start;
-                                A.seg_key[(size_t)c * A.cap_r + rl] = key;
-                                if (key & KEY_NONCANON) atomicOr(&A.hdr->status, SBR_ST_NONCANONICAL);
-                                S.nrec = max(S.nrec, rl + 1);
-                                S.last_end = max(S.last_end, p3 + 1);
-                                if (p3 + 1 >= region_hi) S.done = 1;
+                                const uint32_t p0 = S.first[L - 3], p1 = S.first[L - 2], p2 = S.first[L - 1], p3 = S.first[L];
+                                uint32_t bits = fastq_eval(B, p0, p1, p2, p3, A.bc_len, A.packed, key);
+                                if (p3 + 1 < A.nbytes && B(p3 + 1) != '@') bits |= SBR_ST_INVALID_START;
+                                fastq_commit<FMT>(A, S, c, (L - fo) >> 2, (L == 3) ? region_lo : S.first[L - 4] + 1, p3, key, bits,
+                                                  region_hi);
                             }
+                            S.synced = 1;
                         } else {
                             S.fail = 1;
                         }
                     }
                 }
+                __syncthreads();
             }
-            __syncthreads();  // (3)
-            if (S.synced && !S.fail) {
+            if (S.synced) {
                 const uint32_t h = S.h, fo = S.first_owned;
-                // entries i of this tile that end a record: (h + base + i) % 4 == 3
+                // entries i of this tile that end a record: (h + base + i) % 4 == 3; record u -> thread (u + rot) % 256
                 const uint32_t i0 = (3u - (h + base)) & 3u;
-                for (uint32_t i = i0 + 4u * tid; i < Tw; i += 4u * SCAN_THREADS) {
+                const uint32_t u = ((uint32_t)tid - (it * 64u)) & (SCAN_THREADS - 1);
+                for (uint32_t i = i0 + 4u * u; i < Tw; i += 4u * SCAN_THREADS) {
                     const uint32_t L = base + i;
                     if (L < fo) continue;  // started before this region: the previous region finishes it
-                    const uint32_t start = (L == 3u) ? region_lo : S.list[GHOSTS + (int)i - 4] + 1u;
-                    const uint32_t p3 = S.list[GHOSTS + i];
-                    if (start >= region_hi) continue;  // next region's record (seen while running over)
-                    const uint32_t p2 = S.list[GHOSTS + (int)i - 1], p1 = S.list[GHOSTS + (int)i - 2],
-                                   p0 = S.list[GHOSTS + (int)i - 3];
+                    const uint32_t start = (L == 3u) ? region_lo : list[GHOSTS + (int)i - 4] + 1u;
+                    if (start >= region_hi) continue;  // the next region's record (seen while running over)
+                    const uint32_t p3 = list[GHOSTS + i], p2 = list[GHOSTS + (int)i - 1], p1 = list[GHOSTS + (int)i - 2],
+                                   p0 = list[GHOSTS + (int)i - 3];
                     uint64_t key;
-                    uint32_t bits = fastq_eval(B, p0, p1, p2, p3, A.bc_len, A.packed, key);
-                    if (L == 3u && c == 0 && B(0) != '@') bits |= SBR_ST_INVALID_START;
-                    if (p3 + 1 < A.nbytes && B(p3 + 1) != '@') bits |= SBR_ST_INVALID_START;
-                    const uint32_t rl = (L - fo) >> 2;
-                    if (bits || rl >= A.cap_r) {
-                        S.fail = 1;
-                    } else {
-                        A.seg_rec_off[(size_t)c * A.cap_r + rl] = start;
-                        A.seg_key[(size_t)c * A.cap_r + rl] = key;
-                        if (key & KEY_NONCANON) atomicOr(&A.hdr->status, SBR_ST_NONCANONICAL);
-                        atomicMax(&S.nrec, rl + 1);
-                        atomicMax(&S.last_end, p3 + 1);
-                        if (p3 + 1 >= region_hi) S.done = 1;
+                    uint32_t bits = 0;
+                    bool slow = true;
+                    const bool first_rec = (L == 3u && c == 0);  // record 0 of the batch also checks byte 0
+                    if (p0 > lo && p3 + 1 < lo + valid && (!first_rec || lo == 0)) {
+                        // whole record inside the staged tile: canonical records take the short way
+                        const uint8_t* t = sm - lo;
+                        const uint32_t crs = (t[p0 - 1] == '\r') | (t[p1 - 1] == '\r') | (t[p2 - 1] == '\r') | (t[p3 - 1] == '\r');
+                        const uint32_t seq_len = p1 - p0 - 1;
+                        if (!crs && p2 == p1 + 2 && t[p1 + 1] == '+' && t[p3 + 1] == '@' && seq_len == p3 - p2 - 1 &&
+                            seq_len >= A.bc_len && (!first_rec || sm[0] == '@')) {
+                            key = A.packed ? pack_prefix_vec(sm, p0 + 1 - lo, A.bc_len) : (uint64_t)(p0 + 1);
+                            slow = false;
+                        }
                     }
+                    if (slow) {
+                        bits = fastq_eval(B, p0, p1, p2, p3, A.bc_len, A.packed, key);
+                        if (L == 3u && c == 0 && B(0) != '@') bits |= SBR_ST_INVALID_START;
+                        if (p3 + 1 < A.nbytes && B(p3 + 1) != '@') bits |= SBR_ST_INVALID_START;
+                    }
+                    fastq_commit<FMT>(A, S, c, (L - fo) >> 2, start, p3, key, bits, region_hi);
                 }
             }
         } else {
             // ---- FASTA: thread u handles the u-th record start of the tile --------------------------
-            const uint32_t base = S.rcnt;  // starts seen before this tile (record 0 of the batch not counted)
+            const uint32_t rbase = S.rcnt[par];  // starts seen before this tile (record 0 of the batch not counted)
             const uint32_t own_first = (c == 0) ? 1u : 0u;
-            for (uint32_t u = tid; u < TR; u += SCAN_THREADS) {
-                const uint32_t idx = S.rlist[u];
-                const uint32_t p = S.list[GHOSTS + idx];
-                const uint32_t hint = (idx + 1 < Tw) ? S.list[GHOSTS + idx + 1] : NOPOS;
+            const uint32_t u0 = ((uint32_t)tid - (it * 64u)) & (SCAN_THREADS - 1);
+            for (uint32_t u = u0; u < TR && T <= (uint32_t)FAST_CAP; u += SCAN_THREADS) {  // dense tiles already failed
+                const uint32_t idx = S.rlist[par][u];
+                const uint32_t p = list[GHOSTS + idx];
+                const uint32_t hint = (idx + 1 < Tw) ? list[GHOSTS + idx + 1] : NOPOS;
                 uint64_t key;
                 const uint32_t why = fasta_eval(B, A.nbytes, p + 1, hint, A.bc_len, A.packed, key);
-                const uint32_t rl = base + u + own_first;
+                const uint32_t rl = rbase + u + own_first;
                 // a prefix cut by the end of a non-final batch belongs to the incomplete last record: no error
                 if (rl >= A.cap_r || why == 1 || (why == 2 && A.final_batch)) S.fail = 1;
                 else {
@@ -299,40 +398,27 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
                     A.seg_key[(size_t)c * A.cap_r + rl] = key;
                 }
                 if (u == TR - 1) {
-                    S.last_start_nl = S.cnt + idx + 1;
+                    S.last_start_nl = base + idx + 1;
                     S.last_start_off = p + 1;
                 }
             }
             if (tid == 0 && c == 0 && it == 0) {
                 uint64_t key;
                 if (B(0) != '>') S.fail = 1;
-                const uint32_t why = fasta_eval(B, A.nbytes, 0u, Tw > 0 ? S.list[GHOSTS] : NOPOS, A.bc_len, A.packed, key);
+                const uint32_t why = fasta_eval(B, A.nbytes, 0u, Tw > 0 ? list[GHOSTS] : NOPOS, A.bc_len, A.packed, key);
                 if (why == 1 || (why == 2 && A.final_batch)) S.fail = 1;
                 A.seg_rec_off[0] = 0;
                 A.seg_key[0] = key;
             }
         }
-        __syncthreads();  // (4) all reads of the stage and of the list are done
-        if (tid < GHOSTS) {  // the four most recent newline positions, [GHOSTS-1] the latest
-            uint32_t g = (uint32_t)tid < Tw ? S.list[GHOSTS + Tw - 1 - tid]
-                                            : ((uint32_t)tid - Tw < (uint32_t)GHOSTS ? S.list[GHOSTS - 1 - ((uint32_t)tid - Tw)] : NOPOS);
-            __syncwarp(0xFu);
-            S.list[GHOSTS - 1 - tid] = g;
-        }
-        if (tid == 0) {
-            S.cnt += T;
-            S.rcnt += TR;
-            if (FMT == SBR_FMT_FASTA) S.nl_own = S.cnt;
-            const uint32_t nt = tile + SCAN_STAGES;
-            if (nt < t_hi) issue(s, nt);
-        }
-        __syncthreads();  // (5) state of the next iteration is visible
     }
+    __syncthreads();
 
     if (tid == 0) {
+        const uint32_t n_it = t_hi - t_lo;  // own tiles processed: the final counts sit in parity n_it & 1
         RegionInfo e;
         e.nl_own = S.nl_own;
-        e.nrec = (FMT == SBR_FMT_FASTA) ? S.rcnt + (c == 0 ? 1u : 0u) : S.nrec;
+        e.nrec = (FMT == SBR_FMT_FASTA) ? S.rcnt[n_it & 1u] + (c == 0 ? 1u : 0u) : S.nrec;
         e.phase = (FMT == SBR_FMT_FASTQ && S.synced) ? S.h : PHASE_UNKNOWN;
         e.flags = S.fail ? 1u : 0u;
         e.last_start_nl = S.last_start_nl;
@@ -433,25 +519,31 @@ __global__ void __launch_bounds__(MAX_REGIONS) k_scan_finish(BatchHeader* hdr, R
 
 }  // namespace
 
-size_t scan_fast_smem_bytes() { return (size_t)SCAN_STAGES * SCAN_TILE + sizeof(FastSmem); }
+size_t scan_fast_smem_bytes(uint32_t fmt) {
+    return (size_t)SCAN_STAGES * SCAN_TILE +
+           (fmt == SBR_FMT_FASTA ? sizeof(FastSmem<SBR_FMT_FASTA>) : sizeof(FastSmem<SBR_FMT_FASTQ>));
+}
 
-cudaError_t scan_fast_prepare(int device, int* grid_out) {
+cudaError_t scan_fast_prepare(int device, int* grid_fastq, int* grid_fasta) {
     cudaError_t e;
-    size_t smem = scan_fast_smem_bytes();
-    if ((e = cudaFuncSetAttribute(k_scan_fast<SBR_FMT_FASTQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) !=
-        cudaSuccess)
+    if ((e = cudaFuncSetAttribute(k_scan_fast<SBR_FMT_FASTQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)scan_fast_smem_bytes(SBR_FMT_FASTQ))) != cudaSuccess)
         return e;
-    if ((e = cudaFuncSetAttribute(k_scan_fast<SBR_FMT_FASTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) !=
-        cudaSuccess)
+    if ((e = cudaFuncSetAttribute(k_scan_fast<SBR_FMT_FASTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)scan_fast_smem_bytes(SBR_FMT_FASTA))) != cudaSuccess)
         return e;
-    int per_sm = 0, sms = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_fast<SBR_FMT_FASTQ>, SCAN_THREADS, smem)) !=
-        cudaSuccess)
-        return e;
+    int sms = 0, q = 0, a = 0;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    int g = per_sm * sms;
-    *grid_out = g > MAX_REGIONS ? MAX_REGIONS : g;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_scan_fast<SBR_FMT_FASTQ>, SCAN_THREADS,
+                                                           scan_fast_smem_bytes(SBR_FMT_FASTQ))) != cudaSuccess)
+        return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_scan_fast<SBR_FMT_FASTA>, SCAN_THREADS,
+                                                           scan_fast_smem_bytes(SBR_FMT_FASTA))) != cudaSuccess)
+        return e;
+    q = (q < 1 ? 1 : q) * sms;
+    a = (a < 1 ? 1 : a) * sms;
+    *grid_fastq = q > MAX_REGIONS ? MAX_REGIONS : q;
+    *grid_fasta = a > MAX_REGIONS ? MAX_REGIONS : a;
     return cudaSuccess;
 }
 
@@ -484,11 +576,15 @@ cudaError_t scan_fast_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbyte
     A.bc_len = bc_len;
     A.packed = packed;
     A.final_batch = final_batch;
+    A.c7f = 0x7F7F7F7Fu;
+    A.c0a = 0x0A0A0A0Au;
+    A.c80 = 0x80808080u;
+    A.c3e = 0x3E3E3E3Eu;
     A.hdr = hdr;
     A.info = info;
     A.seg_rec_off = seg_rec_off;
     A.seg_key = seg_key;
-    size_t smem = scan_fast_smem_bytes();
+    size_t smem = scan_fast_smem_bytes(fmt);
     if (fmt == SBR_FMT_FASTQ) {
         k_scan_fast<SBR_FMT_FASTQ><<<n_regions, SCAN_THREADS, smem, stream>>>(A);
         k_scan_finish<SBR_FMT_FASTQ><<<1, MAX_REGIONS, 0, stream>>>(hdr, info, n_regions, nbytes, max_records, final_batch,

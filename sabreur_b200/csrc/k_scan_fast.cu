@@ -28,13 +28,20 @@ namespace sbr {
 namespace {
 
 constexpr uint32_t UNKNOWN_L = 0xFFFFFFFFu;
-constexpr int FAST_CAP = 768;  // newline positions per tile held in shared memory (a 12 KB tile of >= 16-byte lines)
+// One iteration of a CTA covers FAST_UNITS units of SCAN_TILE (12 KB) bytes: every thread masks 48 bytes of
+// each unit, and ONE scan / prefix / barrier pair serves all of them (the fixed per-iteration work is what
+// limits this kernel, see profiles/).
+constexpr int FAST_UNITS = 2;
+constexpr int FAST_TILE = FAST_UNITS * SCAN_TILE;  // 24 KB
+constexpr int FAST_STAGES = 2;
+constexpr int FAST_CAP = 1536;  // newline positions per tile held in shared memory (>= 16-byte lines on average)
 constexpr int LSTRIDE = GHOSTS + FAST_CAP;
 
 template <int FMT>
 struct FastSmem {
-    uint64_t full_bar[SCAN_STAGES];
+    uint64_t full_bar[FAST_STAGES];
     uint32_t warp_tot[SCAN_THREADS / 32];
+    uint32_t warp_tot_r[SCAN_THREADS / 32];
     uint32_t list[2][LSTRIDE];  // double-buffered by tile parity: [GHOSTS + i] = i-th newline, [GHOSTS-1-g] = g-th before the tile
     uint32_t rlist[FMT == SBR_FMT_FASTA ? 2 : 1][FMT == SBR_FMT_FASTA ? FAST_CAP : 1];  // FASTA: list index of record starts
     uint32_t cnt[2];    // newlines seen before the tile, by tile parity
@@ -147,12 +154,13 @@ __device__ __forceinline__ void fastq_commit(const FastArgs& A, FastSmem<FMT>& S
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(SCAN_THREADS, FMT == SBR_FMT_FASTQ ? 4 : 3) k_scan_fast(FastArgs A) {
+__global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     uint8_t* stage_buf = dyn_smem;
-    FastSmem<FMT>& S = *reinterpret_cast<FastSmem<FMT>*>(dyn_smem + SCAN_STAGES * SCAN_TILE);
+    FastSmem<FMT>& S = *reinterpret_cast<FastSmem<FMT>*>(dyn_smem + FAST_STAGES * FAST_TILE);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t c = blockIdx.x;
+    // A.ntiles / tiles_per_region count FAST_TILE-sized tiles
     const uint32_t t_lo = c * A.tiles_per_region + min(c, A.extra_regions);
     const uint32_t t_hi = min(t_lo + A.tiles_per_region + (c < A.extra_regions ? 1u : 0u), A.ntiles);
     if (t_lo >= A.ntiles) {
@@ -162,20 +170,20 @@ __global__ void __launch_bounds__(SCAN_THREADS, FMT == SBR_FMT_FASTQ ? 4 : 3) k_
         }
         return;
     }
-    const uint32_t region_lo = t_lo * (uint32_t)SCAN_TILE;
-    const uint32_t region_hi = min(t_hi * (uint32_t)SCAN_TILE, A.nbytes);
+    const uint32_t region_lo = t_lo * (uint32_t)FAST_TILE;
+    const uint32_t region_hi = min(t_hi * (uint32_t)FAST_TILE, A.nbytes);
     const uint32_t c7f = A.c7f, c0a = A.c0a, c80 = A.c80;
 
     auto issue = [&](int s, uint32_t tile) {  // thread 0 only
-        uint32_t lo = tile * (uint32_t)SCAN_TILE;
-        uint32_t valid = min((uint32_t)SCAN_TILE, A.nbytes - lo);
+        uint32_t lo = tile * (uint32_t)FAST_TILE;
+        uint32_t valid = min((uint32_t)FAST_TILE, A.nbytes - lo);
         uint32_t bytes = (valid + 15u) & ~15u;  // the text buffer is padded to 16 bytes
         mbar_expect_tx(&S.full_bar[s], bytes);
-        bulk_g2s(stage_buf + s * SCAN_TILE, A.text + lo, bytes, &S.full_bar[s]);
+        bulk_g2s(stage_buf + s * FAST_TILE, A.text + lo, bytes, &S.full_bar[s]);
     };
 
     if (tid == 0) {
-        for (int s = 0; s < SCAN_STAGES; ++s) mbar_init(&S.full_bar[s], 1);
+        for (int s = 0; s < FAST_STAGES; ++s) mbar_init(&S.full_bar[s], 1);
         mbar_fence_init();
         S.nfirst = 0;
         S.h = 0;
@@ -195,14 +203,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, FMT == SBR_FMT_FASTQ ? 4 : 3) k_
     }
     __syncthreads();
     if (tid == 0)
-        for (int s = 0; s < SCAN_STAGES; ++s)
+        for (int s = 0; s < FAST_STAGES; ++s)
             if (t_lo + s < t_hi) issue(s, t_lo + s);
 
-    // Tile loop.  Two block barriers per tile: (1) warp totals of the newline scan, (2) newline list complete.
-    // The records of tile t are evaluated by a rotating pair of warps while the other warps already build
-    // the masks of tile t+1; barrier (1) of tile t+1 doubles as "everybody is done with tile t", after which
-    // thread 0 refills tile t's stage.  Past the region's end (FASTQ only: the record left open there) the
-    // same body runs with one more barrier and on-demand loads.
+    // Tile loop.  Two block barriers per 24 KB tile: (1) warp totals of the newline scan, (2) newline list
+    // complete.  The records of tile t are evaluated by a rotating group of warps while the other warps
+    // already build the masks of tile t+1; barrier (1) of tile t+1 doubles as "everybody is done with tile t",
+    // after which thread 0 refills tile t's stage.  Past the region's end (FASTQ only: the record left open
+    // there) the same body runs with one more barrier and on-demand loads.
     for (uint32_t it = 0;; ++it) {
         const uint32_t tile = t_lo + it;
         if (tile >= A.ntiles) break;
@@ -212,84 +220,119 @@ __global__ void __launch_bounds__(SCAN_THREADS, FMT == SBR_FMT_FASTQ ? 4 : 3) k_
             __syncthreads();  // records of the previous tile are complete: S.done / S.synced are final
             if (S.done || !S.synced || S.fail) break;
         }
-        const int s = it % SCAN_STAGES;
+        const int s = it % FAST_STAGES;
         const uint32_t par = it & 1u;
-        const uint32_t parity = (it / SCAN_STAGES) & 1u;
+        const uint32_t parity = (it / FAST_STAGES) & 1u;
         if (overrun && tid == 0) issue(s, tile);  // on demand: one extra tile per region, rarely more
-        const uint32_t lo = tile * (uint32_t)SCAN_TILE;
-        const uint32_t valid = min((uint32_t)SCAN_TILE, A.nbytes - lo);
-        const uint8_t* sm = stage_buf + s * SCAN_TILE;
+        const uint32_t lo = tile * (uint32_t)FAST_TILE;
+        const uint32_t valid = min((uint32_t)FAST_TILE, A.nbytes - lo);
+        const uint8_t* sm = stage_buf + s * FAST_TILE;
         mbar_wait(&S.full_bar[s], parity);
 
-        // ---- newline (and '>') masks of this thread's 48 bytes --------------------------------------
+        // ---- newline (and '>') masks of this thread's 48 bytes in each 12 KB unit -----------------------
         const uint32_t toff = tid * SCAN_BYTES_PER_THREAD;
-        const uint4* src = reinterpret_cast<const uint4*>(sm + toff);
-        const uint4 v0 = src[0], v1 = src[1], v2 = src[2];
-        uint32_t m_lo, m_hi;
-        eq_mask48(v0, v1, v2, c7f, c0a, c80, m_lo, m_hi);
-        uint32_t vm_lo = 0xFFFFFFFFu, vm_hi = 0xFFFFu;
-        if (toff + SCAN_BYTES_PER_THREAD > valid) {
-            uint32_t nv = valid > toff ? valid - toff : 0u;
-            vm_lo = nv >= 32 ? 0xFFFFFFFFu : ((1u << nv) - 1u);
-            vm_hi = nv > 32 ? ((1u << (nv - 32)) - 1u) : 0u;
-            m_lo &= vm_lo;
-            m_hi &= vm_hi;
+        uint32_t m_lo[FAST_UNITS], m_hi[FAST_UNITS], r_lo[FAST_UNITS], r_hi[FAST_UNITS];
+        uint32_t cn2 = 0, cr2 = 0;  // per-unit counts, 16 bits each
+#pragma unroll
+        for (int j = 0; j < FAST_UNITS; ++j) {
+            const uint32_t uoff = j * SCAN_TILE + toff;
+            const uint4* src = reinterpret_cast<const uint4*>(sm + uoff);
+            const uint4 v0 = src[0], v1 = src[1], v2 = src[2];
+            eq_mask48(v0, v1, v2, c7f, c0a, c80, m_lo[j], m_hi[j]);
+            uint32_t vm_lo = 0xFFFFFFFFu, vm_hi = 0xFFFFu;
+            if (uoff + SCAN_BYTES_PER_THREAD > valid) {
+                uint32_t nv = valid > uoff ? valid - uoff : 0u;
+                vm_lo = nv >= 32 ? 0xFFFFFFFFu : ((1u << nv) - 1u);
+                vm_hi = nv > 32 ? ((1u << (nv - 32)) - 1u) : 0u;
+                m_lo[j] &= vm_lo;
+                m_hi[j] &= vm_hi;
+            }
+            r_lo[j] = r_hi[j] = 0;
+            if (FMT == SBR_FMT_FASTA) {
+                uint32_t g_lo, g_hi;
+                eq_mask48(v0, v1, v2, c7f, A.c3e, c80, g_lo, g_hi);
+                g_lo &= vm_lo;
+                g_hi &= vm_hi;
+                const uint32_t nxt = uoff + SCAN_BYTES_PER_THREAD;
+                uint32_t nb = 0;
+                if (nxt < valid) nb = sm[nxt];
+                else if (nxt == (uint32_t)FAST_TILE && lo + nxt < A.nbytes) nb = A.text[lo + nxt];
+                // a record starts after every '\n' that is followed by '>'
+                r_lo[j] = m_lo[j] & ((g_lo >> 1) | (g_hi << 31));
+                r_hi[j] = m_hi[j] & ((g_hi >> 1) | (nb == '>' ? 0x8000u : 0u));
+                cr2 |= (uint32_t)(__popc(r_lo[j]) + __popc(r_hi[j])) << (16 * j);
+            }
+            cn2 |= (uint32_t)(__popc(m_lo[j]) + __popc(m_hi[j])) << (16 * j);
         }
-        uint32_t r_lo = 0, r_hi = 0;
-        if (FMT == SBR_FMT_FASTA) {
-            uint32_t g_lo, g_hi;
-            eq_mask48(v0, v1, v2, c7f, A.c3e, c80, g_lo, g_hi);
-            g_lo &= vm_lo;
-            g_hi &= vm_hi;
-            const uint32_t nxt = toff + SCAN_BYTES_PER_THREAD;
-            uint32_t nb = 0;
-            if (nxt < valid) nb = sm[nxt];
-            else if (nxt == (uint32_t)SCAN_TILE && lo + nxt < A.nbytes) nb = A.text[lo + nxt];
-            // a record starts after every '\n' that is followed by '>'
-            r_lo = m_lo & ((g_lo >> 1) | (g_hi << 31));
-            r_hi = m_hi & ((g_hi >> 1) | (nb == '>' ? 0x8000u : 0u));
+        const uint32_t incl_n = warp_incl_scan(cn2, lane);
+        uint32_t incl_r = 0;
+        if (FMT == SBR_FMT_FASTA) incl_r = warp_incl_scan(cr2, lane);
+        if (lane == 31) {
+            S.warp_tot[warp] = incl_n;
+            if (FMT == SBR_FMT_FASTA) S.warp_tot_r[warp] = incl_r;
         }
-        const uint32_t cn = __popc(m_lo) + __popc(m_hi), cr = __popc(r_lo) + __popc(r_hi);
-        const uint32_t incl2 = warp_incl_scan(cn | (cr << 16), lane);
-        if (lane == 31) S.warp_tot[warp] = incl2;
         __syncthreads();  // (1)
         if (tid == 0 && it >= 1 && !overrun) {  // tile it-1 is finished by everybody: refill its stage
-            const uint32_t nt = tile - 1 + SCAN_STAGES;
-            if (nt < t_hi) issue((it - 1) % SCAN_STAGES, nt);
+            const uint32_t nt = tile - 1 + FAST_STAGES;
+            if (nt < t_hi) issue((it - 1) % FAST_STAGES, nt);
         }
-        uint32_t excl2 = incl2 - (cn | (cr << 16)), T2 = 0;
+        // prefix over the warps by shuffles: lane w holds warp w's totals
+        uint32_t pre_n, tot_n, pre_r = 0, tot_r = 0;
+        {
+            uint32_t t = lane < SCAN_THREADS / 32 ? S.warp_tot[lane] : 0u;
+            uint32_t inc = t;
 #pragma unroll
-        for (int w = 0; w < SCAN_THREADS / 32; ++w) {
-            uint32_t t = S.warp_tot[w];
-            if (w < warp) excl2 += t;
-            T2 += t;
+            for (int d = 1; d < SCAN_THREADS / 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            pre_n = __shfl_sync(0xFFFFFFFFu, inc - t, warp);
+            tot_n = __shfl_sync(0xFFFFFFFFu, inc, SCAN_THREADS / 32 - 1);
+            if (FMT == SBR_FMT_FASTA) {
+                uint32_t tr = lane < SCAN_THREADS / 32 ? S.warp_tot_r[lane] : 0u;
+                uint32_t incr = tr;
+#pragma unroll
+                for (int d = 1; d < SCAN_THREADS / 32; d <<= 1) {
+                    uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incr, d);
+                    if (lane >= d) incr += o;
+                }
+                pre_r = __shfl_sync(0xFFFFFFFFu, incr - tr, warp);
+                tot_r = __shfl_sync(0xFFFFFFFFu, incr, SCAN_THREADS / 32 - 1);
+            }
         }
-        const uint32_t excl = excl2 & 0xFFFFu, T = T2 & 0xFFFFu;
-        const uint32_t excl_r = excl2 >> 16, TR = T2 >> 16;
+        // newline order inside the tile: all of unit 0, then all of unit 1
+        const uint32_t ex2 = pre_n + incl_n - cn2, exr2 = pre_r + incl_r - cr2;
+        const uint32_t T0 = tot_n & 0xFFFFu, T = T0 + (tot_n >> 16);
+        const uint32_t TR0 = tot_r & 0xFFFFu, TR = TR0 + (tot_r >> 16);
         uint32_t* list = S.list[par];
         // read before barrier (2): thread 0 may flip it right after that barrier, and every thread has to
         // take the same decision about the extra barrier below
         const bool was_synced = S.synced != 0;
         // ---- compact newline positions; FASTA also the list index of every record start ---------------
         {
-            uint32_t idx = excl, rk = excl_r;
             bool crlf = false;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t mm = half ? m_hi : m_lo;
-                const uint32_t rr = half ? r_hi : r_lo;
-                while (mm) {
-                    const uint32_t b = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    if (idx < (uint32_t)FAST_CAP) {
-                        list[GHOSTS + idx] = lo + toff + 32 * half + b;
-                        if (FMT == SBR_FMT_FASTA) {
-                            if ((rr >> b) & 1u) S.rlist[par][rk++] = idx;
-                            const uint32_t o = toff + 32 * half + b;  // CR before LF makes a FASTA batch non-canonical
-                            crlf |= o > 0 ? sm[o - 1] == '\r' : (lo > 0 && A.text[lo - 1] == '\r');
+            for (int j = 0; j < FAST_UNITS; ++j) {
+                uint32_t idx = j ? T0 + (ex2 >> 16) : (ex2 & 0xFFFFu);
+                uint32_t rk = j ? TR0 + (exr2 >> 16) : (exr2 & 0xFFFFu);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t mm = half ? m_hi[j] : m_lo[j];
+                    const uint32_t rr = half ? r_hi[j] : r_lo[j];
+                    const uint32_t o0 = j * SCAN_TILE + toff + 32 * half;
+                    while (mm) {
+                        const uint32_t b = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        if (idx < (uint32_t)FAST_CAP) {
+                            list[GHOSTS + idx] = lo + o0 + b;
+                            if (FMT == SBR_FMT_FASTA) {
+                                if ((rr >> b) & 1u) S.rlist[par][rk++] = idx;
+                                const uint32_t o = o0 + b;  // CR before LF makes a FASTA batch non-canonical
+                                crlf |= o > 0 ? sm[o - 1] == '\r' : (lo > 0 && A.text[lo - 1] == '\r');
+                            }
                         }
+                        ++idx;
                     }
-                    ++idx;
                 }
             }
             if (FMT == SBR_FMT_FASTA && crlf) S.crlf = 1;
@@ -348,7 +391,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, FMT == SBR_FMT_FASTQ ? 4 : 3) k_
                 const uint32_t h = S.h, fo = S.first_owned;
                 // entries i of this tile that end a record: (h + base + i) % 4 == 3; record u -> thread (u + rot) % 256
                 const uint32_t i0 = (3u - (h + base)) & 3u;
-                const uint32_t u = ((uint32_t)tid - (it * 64u)) & (SCAN_THREADS - 1);
+                const uint32_t u = ((uint32_t)tid - (it * 96u)) & (SCAN_THREADS - 1);
                 for (uint32_t i = i0 + 4u * u; i < Tw; i += 4u * SCAN_THREADS) {
                     const uint32_t L = base + i;
                     if (L < fo) continue;  // started before this region: the previous region finishes it
@@ -356,24 +399,32 @@ __global__ void __launch_bounds__(SCAN_THREADS, FMT == SBR_FMT_FASTQ ? 4 : 3) k_
                     if (start >= region_hi) continue;  // the next region's record (seen while running over)
                     const uint32_t p3 = list[GHOSTS + i], p2 = list[GHOSTS + (int)i - 1], p1 = list[GHOSTS + (int)i - 2],
                                    p0 = list[GHOSTS + (int)i - 3];
-                    uint64_t key;
+                    uint64_t key = 0;
                     uint32_t bits = 0;
-                    bool slow = true;
                     const bool first_rec = (L == 3u && c == 0);  // record 0 of the batch also checks byte 0
-                    if (p0 > lo && p3 + 1 < lo + valid && (!first_rec || lo == 0)) {
-                        // whole record inside the staged tile: canonical records take the short way
-                        const uint8_t* t = sm - lo;
-                        const uint32_t crs = (t[p0 - 1] == '\r') | (t[p1 - 1] == '\r') | (t[p2 - 1] == '\r') | (t[p3 - 1] == '\r');
-                        const uint32_t seq_len = p1 - p0 - 1;
-                        if (!crs && p2 == p1 + 2 && t[p1 + 1] == '+' && t[p3 + 1] == '@' && seq_len == p3 - p2 - 1 &&
-                            seq_len >= A.bc_len && (!first_rec || sm[0] == '@')) {
-                            key = A.packed ? pack_prefix_vec(sm, p0 + 1 - lo, A.bc_len) : (uint64_t)(p0 + 1);
-                            slow = false;
+                    const bool inside = p0 > lo && p3 + 1 < lo + valid;
+                    // canonical record (LF ends, bare '+', equal lengths, long enough, next record's '@'):
+                    // six byte probes; anything else goes through the general evaluation
+                    const uint32_t seq_len = p1 - p0 - 1;
+                    bool canon = p2 == p1 + 2 && seq_len == p3 - p2 - 1 && seq_len >= A.bc_len && p0 > 0;
+                    if (canon) {
+                        if (inside) {
+                            const uint8_t* t = sm - lo;
+                            canon = t[p0 - 1] != '\r' && t[p1 - 1] != '\r' && t[p3 - 1] != '\r' && t[p1 + 1] == '+' &&
+                                    t[p3 + 1] == '@';
+                        } else {
+                            canon = B(p0 - 1) != '\r' && B(p1 - 1) != '\r' && B(p3 - 1) != '\r' && B(p1 + 1) == '+' &&
+                                    (p3 + 1 >= A.nbytes || B(p3 + 1) == '@');
                         }
+                        if (first_rec) canon = canon && A.text[0] == '@';
                     }
-                    if (slow) {
+                    if (canon) {
+                        if (!A.packed) key = (uint64_t)(p0 + 1);
+                        else if (p0 + 1 >= lo) key = pack_prefix_vec(sm, p0 + 1 - lo, A.bc_len);  // p1 < lo + valid here
+                        else key = pack_prefix(B, p0 + 1, A.bc_len);
+                    } else {
                         bits = fastq_eval(B, p0, p1, p2, p3, A.bc_len, A.packed, key);
-                        if (L == 3u && c == 0 && B(0) != '@') bits |= SBR_ST_INVALID_START;
+                        if (first_rec && B(0) != '@') bits |= SBR_ST_INVALID_START;
                         if (p3 + 1 < A.nbytes && B(p3 + 1) != '@') bits |= SBR_ST_INVALID_START;
                     }
                     fastq_commit<FMT>(A, S, c, (L - fo) >> 2, start, p3, key, bits, region_hi);
@@ -383,7 +434,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, FMT == SBR_FMT_FASTQ ? 4 : 3) k_
             // ---- FASTA: thread u handles the u-th record start of the tile --------------------------
             const uint32_t rbase = S.rcnt[par];  // starts seen before this tile (record 0 of the batch not counted)
             const uint32_t own_first = (c == 0) ? 1u : 0u;
-            const uint32_t u0 = ((uint32_t)tid - (it * 64u)) & (SCAN_THREADS - 1);
+            const uint32_t u0 = ((uint32_t)tid - (it * 96u)) & (SCAN_THREADS - 1);
             for (uint32_t u = u0; u < TR && T <= (uint32_t)FAST_CAP; u += SCAN_THREADS) {  // dense tiles already failed
                 const uint32_t idx = S.rlist[par][u];
                 const uint32_t p = list[GHOSTS + idx];
@@ -520,7 +571,7 @@ __global__ void __launch_bounds__(MAX_REGIONS) k_scan_finish(BatchHeader* hdr, R
 }  // namespace
 
 size_t scan_fast_smem_bytes(uint32_t fmt) {
-    return (size_t)SCAN_STAGES * SCAN_TILE +
+    return (size_t)FAST_STAGES * FAST_TILE +
            (fmt == SBR_FMT_FASTA ? sizeof(FastSmem<SBR_FMT_FASTA>) : sizeof(FastSmem<SBR_FMT_FASTQ>));
 }
 
@@ -547,12 +598,12 @@ cudaError_t scan_fast_prepare(int device, int* grid_fastq, int* grid_fasta) {
     return cudaSuccess;
 }
 
-// Regions of a batch: at most max_regions CTAs, at least 8 tiles (96 KB) each so that the work at a
+// Regions of a batch: at most max_regions CTAs, at least 4 tiles (96 KB) each so that the work at a
 // region's start and end is amortised and every region sees enough newlines to find its phase; the
 // tiles that do not divide evenly go one each to the first regions.
 uint32_t scan_fast_regions(uint32_t nbytes, int max_regions, uint32_t* tiles_per_region, uint32_t* extra_regions) {
-    const uint32_t ntiles = (nbytes + SCAN_TILE - 1) / SCAN_TILE;
-    const uint32_t min_tiles = 8;
+    const uint32_t ntiles = (nbytes + FAST_TILE - 1) / FAST_TILE;
+    const uint32_t min_tiles = 4;
     uint32_t R = ntiles / min_tiles;
     if (R > (uint32_t)max_regions) R = (uint32_t)max_regions;
     if (R == 0) R = 1;
@@ -569,7 +620,7 @@ cudaError_t scan_fast_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbyte
     FastArgs A;
     A.text = d_text;
     A.nbytes = nbytes;
-    A.ntiles = (nbytes + SCAN_TILE - 1) / SCAN_TILE;
+    A.ntiles = (nbytes + FAST_TILE - 1) / FAST_TILE;
     A.tiles_per_region = tiles_per_region;
     A.extra_regions = extra_regions;
     A.cap_r = cap_r;

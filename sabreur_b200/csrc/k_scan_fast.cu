@@ -35,15 +35,17 @@ constexpr int FAST_UNITS = 2;
 constexpr int FAST_TILE = FAST_UNITS * SCAN_TILE;  // 24 KB
 constexpr int FAST_STAGES = 2;
 constexpr int FAST_CAP = 1536;  // newline positions per tile held in shared memory (>= 16-byte lines on average)
-constexpr int LSTRIDE = GHOSTS + FAST_CAP;
 
 template <int FMT>
 struct FastSmem {
     uint64_t full_bar[FAST_STAGES];
     uint32_t warp_tot[SCAN_THREADS / 32];
     uint32_t warp_tot_r[SCAN_THREADS / 32];
-    uint32_t list[2][LSTRIDE];  // double-buffered by tile parity: [GHOSTS + i] = i-th newline, [GHOSTS-1-g] = g-th before the tile
-    uint32_t rlist[FMT == SBR_FMT_FASTA ? 2 : 1][FMT == SBR_FMT_FASTA ? FAST_CAP : 1];  // FASTA: list index of record starts
+    // newline positions of the current tile.  One buffer is enough: it is rewritten after barrier (1) of the
+    // next tile, which every thread reaches only after it has finished this tile's records.
+    uint32_t list[FAST_CAP];
+    uint32_t ghost[2][GHOSTS];  // by tile parity: [g] = g-th most recent newline before the tile
+    uint32_t rlist[FMT == SBR_FMT_FASTA ? FAST_CAP : 1];  // FASTA: list index of record starts
     uint32_t cnt[2];    // newlines seen before the tile, by tile parity
     uint32_t rcnt[2];   // FASTA: record starts seen before the tile
     uint32_t first[8];  // FASTQ: the region's first eight newline positions
@@ -154,7 +156,7 @@ __device__ __forceinline__ void fastq_commit(const FastArgs& A, FastSmem<FMT>& S
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
+__global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     uint8_t* stage_buf = dyn_smem;
     FastSmem<FMT>& S = *reinterpret_cast<FastSmem<FMT>*>(dyn_smem + FAST_STAGES * FAST_TILE);
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
         S.last_start_nl = 0;
         S.last_start_off = 0;
         S.crlf = 0;
-        for (int g = 0; g < GHOSTS; ++g) S.list[0][g] = NOPOS;
+        for (int g = 0; g < GHOSTS; ++g) S.ghost[0][g] = NOPOS;
     }
     __syncthreads();
     if (tid == 0)
@@ -304,7 +306,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
         const uint32_t ex2 = pre_n + incl_n - cn2, exr2 = pre_r + incl_r - cr2;
         const uint32_t T0 = tot_n & 0xFFFFu, T = T0 + (tot_n >> 16);
         const uint32_t TR0 = tot_r & 0xFFFFu, TR = TR0 + (tot_r >> 16);
-        uint32_t* list = S.list[par];
+        uint32_t* list = S.list;
+        const uint32_t* ghost = S.ghost[par];
         // read before barrier (2): thread 0 may flip it right after that barrier, and every thread has to
         // take the same decision about the extra barrier below
         const bool was_synced = S.synced != 0;
@@ -324,9 +327,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
                         const uint32_t b = __ffs(mm) - 1;
                         mm &= mm - 1;
                         if (idx < (uint32_t)FAST_CAP) {
-                            list[GHOSTS + idx] = lo + o0 + b;
+                            list[idx] = lo + o0 + b;
                             if (FMT == SBR_FMT_FASTA) {
-                                if ((rr >> b) & 1u) S.rlist[par][rk++] = idx;
+                                if ((rr >> b) & 1u) S.rlist[rk++] = idx;
                                 const uint32_t o = o0 + b;  // CR before LF makes a FASTA batch non-canonical
                                 crlf |= o > 0 ? sm[o - 1] == '\r' : (lo > 0 && A.text[lo - 1] == '\r');
                             }
@@ -345,8 +348,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
         const uint32_t base = S.cnt[par];
         // ---- state of the next tile (other parity): count and the four most recent newline positions ----
         if (tid < GHOSTS) {
-            const uint32_t g = (uint32_t)tid < Tw ? list[GHOSTS + Tw - 1 - tid] : list[GHOSTS - 1 - ((uint32_t)tid - Tw)];
-            S.list[par ^ 1u][GHOSTS - 1 - tid] = g;
+            const uint32_t g = (uint32_t)tid < Tw ? list[Tw - 1 - tid] : ghost[(uint32_t)tid - Tw];
+            S.ghost[par ^ 1u][tid] = g;
             if (tid == 0) {
                 S.cnt[par ^ 1u] = base + T;
                 S.rcnt[par ^ 1u] = S.rcnt[par] + TR;
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
             if (!was_synced) {  // uniform: only the first tile(s) of a region, until eight newlines were seen
                 if (tid == 0) {
                     uint32_t nf = S.nfirst;
-                    for (uint32_t i = 0; i < Tw && nf < 8; ++i) S.first[nf++] = list[GHOSTS + i];
+                    for (uint32_t i = 0; i < Tw && nf < 8; ++i) S.first[nf++] = list[i];
                     S.nfirst = nf;
                     if (nf >= 8) {
                         uint32_t h;
@@ -395,10 +398,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
                 for (uint32_t i = i0 + 4u * u; i < Tw; i += 4u * SCAN_THREADS) {
                     const uint32_t L = base + i;
                     if (L < fo) continue;  // started before this region: the previous region finishes it
-                    const uint32_t start = (L == 3u) ? region_lo : list[GHOSTS + (int)i - 4] + 1u;
+                    // entry i - d of the newline stream: this tile's list, or the ghosts of earlier tiles
+                    auto nl = [&](uint32_t d) -> uint32_t { return i >= d ? list[i - d] : ghost[d - i - 1]; };
+                    const uint32_t start = (L == 3u) ? region_lo : nl(4) + 1u;
                     if (start >= region_hi) continue;  // the next region's record (seen while running over)
-                    const uint32_t p3 = list[GHOSTS + i], p2 = list[GHOSTS + (int)i - 1], p1 = list[GHOSTS + (int)i - 2],
-                                   p0 = list[GHOSTS + (int)i - 3];
+                    const uint32_t p3 = list[i], p2 = nl(1), p1 = nl(2), p0 = nl(3);
                     uint64_t key = 0;
                     uint32_t bits = 0;
                     const bool first_rec = (L == 3u && c == 0);  // record 0 of the batch also checks byte 0
@@ -408,10 +412,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
                     const uint32_t seq_len = p1 - p0 - 1;
                     bool canon = p2 == p1 + 2 && seq_len == p3 - p2 - 1 && seq_len >= A.bc_len && p0 > 0;
                     if (canon) {
-                        if (inside) {
+                        if (inside) {  // five independent probes, combined without short-circuit branches
                             const uint8_t* t = sm - lo;
-                            canon = t[p0 - 1] != '\r' && t[p1 - 1] != '\r' && t[p3 - 1] != '\r' && t[p1 + 1] == '+' &&
-                                    t[p3 + 1] == '@';
+                            const uint32_t b0 = t[p0 - 1], b1 = t[p1 - 1], b3 = t[p3 - 1], bp = t[p1 + 1], bn = t[p3 + 1];
+                            canon = (b0 != '\r') & (b1 != '\r') & (b3 != '\r') & (bp == '+') & (bn == '@');
                         } else {
                             canon = B(p0 - 1) != '\r' && B(p1 - 1) != '\r' && B(p3 - 1) != '\r' && B(p1 + 1) == '+' &&
                                     (p3 + 1 >= A.nbytes || B(p3 + 1) == '@');
@@ -436,9 +440,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
             const uint32_t own_first = (c == 0) ? 1u : 0u;
             const uint32_t u0 = ((uint32_t)tid - (it * 96u)) & (SCAN_THREADS - 1);
             for (uint32_t u = u0; u < TR && T <= (uint32_t)FAST_CAP; u += SCAN_THREADS) {  // dense tiles already failed
-                const uint32_t idx = S.rlist[par][u];
-                const uint32_t p = list[GHOSTS + idx];
-                const uint32_t hint = (idx + 1 < Tw) ? list[GHOSTS + idx + 1] : NOPOS;
+                const uint32_t idx = S.rlist[u];
+                const uint32_t p = list[idx];
+                const uint32_t hint = (idx + 1 < Tw) ? list[idx + 1] : NOPOS;
                 uint64_t key;
                 const uint32_t why = fasta_eval(B, A.nbytes, p + 1, hint, A.bc_len, A.packed, key);
                 const uint32_t rl = rbase + u + own_first;
@@ -456,7 +460,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_fast(FastArgs A) {
             if (tid == 0 && c == 0 && it == 0) {
                 uint64_t key;
                 if (B(0) != '>') S.fail = 1;
-                const uint32_t why = fasta_eval(B, A.nbytes, 0u, Tw > 0 ? list[GHOSTS] : NOPOS, A.bc_len, A.packed, key);
+                const uint32_t why = fasta_eval(B, A.nbytes, 0u, Tw > 0 ? list[0] : NOPOS, A.bc_len, A.packed, key);
                 if (why == 1 || (why == 2 && A.final_batch)) S.fail = 1;
                 A.seg_rec_off[0] = 0;
                 A.seg_key[0] = key;

@@ -49,8 +49,8 @@ struct PartitionPlan {
 PartitionPlan partition_plan(uint32_t nbins, uint32_t max_records, int sms);
 cudaError_t partition_prepare();
 cudaError_t partition_launch(const uint16_t* d_assign, const BatchHeader* d_hdr, uint32_t nbins, uint32_t* d_cnt,
-                             uint32_t* d_bin_count, uint32_t* d_bin_start, uint32_t* d_order, const PartitionPlan& p,
-                             cudaStream_t stream);
+                             uint32_t* d_bin_count, uint32_t* d_bin_start, uint32_t* d_order, uint32_t* d_done_counter,
+                             const PartitionPlan& p, cudaStream_t stream);
 }  // namespace sbr
 
 using namespace sbr;
@@ -79,6 +79,7 @@ struct Slot {
     uint32_t* d_region_base = nullptr;
     uint32_t* d_seg_rec_off = nullptr;
     uint64_t* d_seg_key = nullptr;
+    uint32_t* d_done = nullptr;  // k_binscan's last-block counter (self-resetting)
     // pinned host
     uint8_t* h_text = nullptr;
     BatchHeader* h_hdr = nullptr;
@@ -168,7 +169,7 @@ extern "C" const char* sbr_last_error(const sbr_ctx* ctx) { return ctx ? ctx->er
 static void free_slot(Slot& s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFree(s.d_text); cudaFree(s.d_hdr); cudaFree(s.d_desc); cudaFree(s.d_rec_off); cudaFree(s.d_key);
-    cudaFree(s.d_info); cudaFree(s.d_region_base); cudaFree(s.d_seg_rec_off); cudaFree(s.d_seg_key);
+    cudaFree(s.d_done); cudaFree(s.d_info); cudaFree(s.d_region_base); cudaFree(s.d_seg_rec_off); cudaFree(s.d_seg_key);
     cudaFree(s.d_assign); cudaFree(s.d_cnt); cudaFree(s.d_bin_count); cudaFree(s.d_bin_start); cudaFree(s.d_order);
     cudaFreeHost(s.h_text); cudaFreeHost(s.h_hdr); cudaFreeHost(s.h_rec_off); cudaFreeHost(s.h_key);
     cudaFreeHost(s.h_assign); cudaFreeHost(s.h_bin_count); cudaFreeHost(s.h_bin_start); cudaFreeHost(s.h_order);
@@ -276,6 +277,8 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
         CU(c, cudaMalloc(&s.d_bin_count, c->nbins * sizeof(uint32_t)));
         CU(c, cudaMalloc(&s.d_bin_start, (c->nbins + 1) * sizeof(uint32_t)));
         CU(c, cudaMalloc(&s.d_order, (mr + 1) * sizeof(uint32_t)));
+        CU(c, cudaMalloc(&s.d_done, sizeof(uint32_t)));
+        CU(c, cudaMemset(s.d_done, 0, sizeof(uint32_t)));
         CU(c, cudaMalloc(&s.d_info, MAX_REGIONS * sizeof(RegionInfo)));
         CU(c, cudaMalloc(&s.d_region_base, (MAX_REGIONS + 1) * sizeof(uint32_t)));
         const size_t seg = mr * 5 / 4 + 65 * (size_t)MAX_REGIONS;
@@ -370,9 +373,10 @@ static int launch_pipeline(sbr_ctx* c, Slot& s, const uint8_t* d_text, uint32_t 
         CU(c, match_launch(L, st));
     }
     if (ev) CU(c, cudaEventRecord(ev[2], st));
-    CU(c, partition_launch(s.d_assign, s.d_hdr, c->nbins, s.d_cnt, s.d_bin_count, s.d_bin_start, s.d_order, c->plan, st));
+    CU(c, partition_launch(s.d_assign, s.d_hdr, c->nbins, s.d_cnt, s.d_bin_count, s.d_bin_start, s.d_order, s.d_done,
+                           c->plan, st));
     if (ev) CU(c, cudaEventRecord(ev[3], st));
-    c->launches += (fmt == SBR_FMT_FASTA ? 2 : 1) + 1 + 3;  // look-back scan (+finish), match, partition
+    c->launches += (fmt == SBR_FMT_FASTA ? 2 : 1) + 1 + 2;  // look-back scan (+finish), match, partition
     return SBR_OK;
 }
 

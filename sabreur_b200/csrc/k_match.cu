@@ -110,46 +110,72 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(RecSource src, const Ba
     uint32_t* mine = s_hist + (size_t)warp * nbins;
     uint32_t lo, hi;
     slice_range(nrec, V, v, lo, hi);
-    for (uint32_t g = lo + lane; g < hi; g += 32) {
-        uint64_t kk;
-        if (mode) {
-            uint32_t a = 0, b = nreg;  // largest c with s_base[c] <= g
-            while (b - a > 1) {
-                uint32_t mid = (a + b) >> 1;
-                if (s_base[mid] <= g) a = mid; else b = mid;
-            }
-            size_t at = (size_t)a * src.cap_r + (g - s_base[a]);
-            kk = src.seg_key[at];
-            rec_off[g] = src.seg_rec_off[at];
-            if (want_keys) key_out[g] = kk;
-        } else {
-            kk = src.key_dense[g];
-        }
-        uint32_t hit = n;
-        if (!(kk & KEY_SHORT)) {  // short reads are reported by the scan; the host aborts like the reference's panic
-            if (MODE == 2) {
-                uint8_t pre[64];
-                uint32_t q = (uint32_t)kk, got = 0;
-                while (got < k && q < nbytes) {  // FASTA sequences may wrap lines inside the window
-                    uint8_t c = text[q++];
-                    if (fasta && (c == '\n' || (c == '\r' && q < nbytes && text[q] == '\n'))) continue;
-                    pre[got++] = c;
+    // four records per lane and step: all loads of a step are issued before the first use
+    constexpr int U = 4;
+    uint32_t reg_lo = 1, reg_hi = 0;  // record range [reg_lo, reg_hi) of the region found last, and where its segment starts
+    size_t reg_at = 0;
+    for (uint32_t g0 = lo; g0 < hi; g0 += 32 * U) {
+        uint64_t kk[U];
+        uint32_t ro[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t g = g0 + u * 32 + lane;
+            kk[u] = KEY_SHORT;
+            ro[u] = 0;
+            if (g < hi) {
+                if (mode) {
+                    if (g < reg_lo || g >= reg_hi) {  // regions hold thousands of records: rarely taken
+                        uint32_t a = 0, b = nreg;     // largest c with s_base[c] <= g
+                        while (b - a > 1) {
+                            uint32_t mid = (a + b) >> 1;
+                            if (s_base[mid] <= g) a = mid; else b = mid;
+                        }
+                        reg_lo = s_base[a];
+                        reg_hi = s_base[a + 1];
+                        reg_at = (size_t)a * src.cap_r;
+                    }
+                    const size_t at = reg_at + (g - reg_lo);
+                    kk[u] = ld_stream_u64(src.seg_key + at);
+                    ro[u] = src.seg_rec_off[at];
+                } else {
+                    kk[u] = src.key_dense[g];
                 }
-                for (uint32_t b = 0; b < n && hit == n; ++b) {
-                    const uint8_t* row = s_rows + (size_t)b * stride;
-                    uint32_t mis = 0;
-                    for (uint32_t j = 0; j < s_lens[b]; ++j) mis += (row[j] != pre[j]);
-                    if (mis <= m) hit = b;
-                }
-            } else {
-                uint32_t codes = (uint32_t)kk & code_mask;
-                uint32_t inval = (uint32_t)(kk >> 32) & 0xFFFFu;
-                if (MODE == 0 && inval == 0) hit = __ldg(lut + codes);
-                else hit = first_match(s_tab, n, m, codes, spread16(inval));
             }
         }
-        assign[g] = (uint16_t)hit;
-        atomicAdd(&mine[hit], 1u);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t g = g0 + u * 32 + lane;
+            if (g >= hi) continue;
+            uint32_t hit = n;
+            if (!(kk[u] & KEY_SHORT)) {  // short reads are reported by the scan; the host aborts like the reference's panic
+                if (MODE == 2) {
+                    uint8_t pre[64];
+                    uint32_t q = (uint32_t)kk[u], got = 0;
+                    while (got < k && q < nbytes) {  // FASTA sequences may wrap lines inside the window
+                        uint8_t c = text[q++];
+                        if (fasta && (c == '\n' || (c == '\r' && q < nbytes && text[q] == '\n'))) continue;
+                        pre[got++] = c;
+                    }
+                    for (uint32_t b = 0; b < n && hit == n; ++b) {
+                        const uint8_t* row = s_rows + (size_t)b * stride;
+                        uint32_t mis = 0;
+                        for (uint32_t j = 0; j < s_lens[b]; ++j) mis += (row[j] != pre[j]);
+                        if (mis <= m) hit = b;
+                    }
+                } else {
+                    uint32_t codes = (uint32_t)kk[u] & code_mask;
+                    uint32_t inval = (uint32_t)(kk[u] >> 32) & 0xFFFFu;
+                    if (MODE == 0 && inval == 0) hit = __ldg(lut + codes);
+                    else hit = first_match(s_tab, n, m, codes, spread16(inval));
+                }
+            }
+            assign[g] = (uint16_t)hit;
+            if (mode) {
+                rec_off[g] = ro[u];
+                if (want_keys) key_out[g] = kk[u];
+            }
+            atomicAdd(&mine[hit], 1u);
+        }
     }
     __syncwarp();
     for (uint32_t b = lane; b < nbins; b += 32) cnt[(size_t)b * V + v] = mine[b];

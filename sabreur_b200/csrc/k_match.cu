@@ -145,10 +145,11 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(RecSource src, const Ba
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t g = g0 + u * 32 + lane;
-            if (g >= hi) continue;
+            const bool live = g < hi;
             uint32_t hit = n;
-            if (!(kk[u] & KEY_SHORT)) {  // short reads are reported by the scan; the host aborts like the reference's panic
-                if (MODE == 2) {
+            const bool usable = live && !(kk[u] & KEY_SHORT);  // short reads are reported by the scan (the reference panics)
+            if (MODE == 2) {
+                if (usable) {
                     uint8_t pre[64];
                     uint32_t q = (uint32_t)kk[u], got = 0;
                     while (got < k && q < nbytes) {  // FASTA sequences may wrap lines inside the window
@@ -162,19 +163,46 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(RecSource src, const Ba
                         for (uint32_t j = 0; j < s_lens[b]; ++j) mis += (row[j] != pre[j]);
                         if (mis <= m) hit = b;
                     }
+                }
+            } else {
+                const uint32_t codes = (uint32_t)kk[u] & code_mask;
+                const uint32_t inval = (uint32_t)(kk[u] >> 32) & 0xFFFFu;
+                if (MODE == 1) {
+                    if (usable) hit = first_match(s_tab, n, m, codes, spread16(inval));
                 } else {
-                    uint32_t codes = (uint32_t)kk[u] & code_mask;
-                    uint32_t inval = (uint32_t)(kk[u] >> 32) & 0xFFFFu;
-                    if (MODE == 0 && inval == 0) hit = __ldg(lut + codes);
-                    else hit = first_match(s_tab, n, m, codes, spread16(inval));
+                    if (usable && inval == 0) hit = __ldg(lut + codes);
+                    // reads with a non-ACGT base in the window (rare) cannot use the LUT: the warp walks the
+                    // table together, 32 rows per step, one such read at a time
+                    uint32_t todo = __ballot_sync(0xFFFFFFFFu, usable && inval != 0);
+                    while (todo) {
+                        const int srcl = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const uint32_t cs = __shfl_sync(0xFFFFFFFFu, codes, srcl);
+                        const uint32_t is = spread16(__shfl_sync(0xFFFFFFFFu, inval, srcl));
+                        uint32_t found = n;
+                        for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+                            const uint32_t b = b0 + lane;
+                            bool ok = false;
+                            if (b < n) {
+                                const uint2 row = s_tab[b];
+                                const uint32_t x = cs ^ row.x;
+                                ok = (uint32_t)__popc(((x | (x >> 1)) | is) & row.y) <= m;
+                            }
+                            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, ok);
+                            if (bal) { found = b0 + __ffs(bal) - 1; break; }
+                        }
+                        if (lane == srcl) hit = found;
+                    }
                 }
             }
-            assign[g] = (uint16_t)hit;
-            if (mode) {
-                rec_off[g] = ro[u];
-                if (want_keys) key_out[g] = kk[u];
+            if (live) {
+                assign[g] = (uint16_t)hit;
+                if (mode) {
+                    rec_off[g] = ro[u];
+                    if (want_keys) key_out[g] = kk[u];
+                }
+                atomicAdd(&mine[hit], 1u);
             }
-            atomicAdd(&mine[hit], 1u);
         }
     }
     __syncwarp();

@@ -42,24 +42,27 @@ __global__ void __launch_bounds__(PART_THREADS) k_binscan(uint32_t* __restrict__
     __shared__ uint32_t s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* row = cnt + (size_t)blockIdx.x * V;
-    const uint32_t per = (V + PART_THREADS - 1) / PART_THREADS;
-    const uint32_t i0 = min(threadIdx.x * per, V), i1 = min(i0 + per, V);
+    // every warp owns a contiguous run of slices and walks it 32 at a time (coalesced)
+    const uint32_t per = (((V + PART_WARPS - 1) / PART_WARPS) + 31u) & ~31u;
+    const uint32_t w0 = min((uint32_t)warp * per, V), w1 = min(w0 + per, V);
     uint32_t sum = 0;
-    for (uint32_t i = i0; i < i1; ++i) sum += row[i];
-    uint32_t inc = warp_incl_scan(sum, lane);
-    if (lane == 31) s_warp[warp] = inc;
+    for (uint32_t i = w0 + lane; i < w1; i += 32) sum += row[i];
+    sum = warp_sum(sum);
+    if (lane == 0) s_warp[warp] = sum;
     __syncthreads();
-    uint32_t pre = inc - sum, tot = 0;
+    uint32_t carry = 0, tot = 0;
 #pragma unroll
     for (int w = 0; w < PART_WARPS; ++w) {
         uint32_t t = s_warp[w];
-        if (w < warp) pre += t;
+        if (w < warp) carry += t;
         tot += t;
     }
-    for (uint32_t i = i0; i < i1; ++i) {
-        uint32_t x = row[i];
-        row[i] = pre;
-        pre += x;
+    for (uint32_t i0 = w0; i0 < w1; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const uint32_t x = i < w1 ? row[i] : 0u;
+        const uint32_t inc = warp_incl_scan(x, lane);
+        if (i < w1) row[i] = carry + inc - x;
+        carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
     }
     if (threadIdx.x == 0) {
         bin_count[blockIdx.x] = tot;

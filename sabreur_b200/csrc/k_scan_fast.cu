@@ -7,8 +7,13 @@
 // 32 tiles per L2 round trip, which caps a newline-count scan near 0.45 TB/s on B200 (measured, see
 // DESIGN.md).  Here nothing on the critical path waits on another CTA:
 //   * the batch is cut into one contiguous region per CTA; the CTA streams its region tile by tile
-//     through a ring of 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP) completing on mbarriers,
-//     and carries its own running state (newline count, last four newline positions) in shared memory;
+//     through a ring of 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP) completing on mbarriers;
+//   * inside a tile every WARP owns a contiguous 3 KB slice: it builds the newline masks of its slice,
+//     compacts the newline positions into a warp-private list and evaluates the records that END in
+//     its slice, one lane per record.  The only things a warp needs from the others are how many
+//     newlines precede its slice (its place in the 4-line cycle) and the last four newline positions
+//     before it; both are published before the ONE block barrier of the tile, so every warp carries
+//     the same load between barriers;
 //   * FASTQ: where in the 4-line cycle a region starts is not known locally ('@' and '+' are legal
 //     quality characters), so the CTA DETECTS it from its first eight newlines (the one phase under
 //     which the first whole record parses) and k_scan_finish VERIFIES every region's phase against the
@@ -28,26 +33,26 @@ namespace sbr {
 namespace {
 
 constexpr uint32_t UNKNOWN_L = 0xFFFFFFFFu;
-// One iteration of a CTA covers FAST_UNITS units of SCAN_TILE (12 KB) bytes: every thread masks 48 bytes of
-// each unit, and ONE scan / prefix / barrier pair serves all of them (the fixed per-iteration work is what
-// limits this kernel, see profiles/).
+constexpr int FAST_WARPS = SCAN_THREADS / 32;
+// A lane masks 48 bytes in each of FAST_UNITS units of its warp's slice; one warp scan serves all of them.
 constexpr int FAST_UNITS = 2;
-constexpr int FAST_TILE = FAST_UNITS * SCAN_TILE;  // 24 KB
+constexpr int UNIT_BYTES = 32 * SCAN_BYTES_PER_THREAD;  // 1536 B: one 48-byte chunk per lane
+constexpr int WARP_SLICE = FAST_UNITS * UNIT_BYTES;     // 3072 B
+constexpr int FAST_TILE = FAST_WARPS * WARP_SLICE;      // 24 KB
 constexpr int FAST_STAGES = 2;
-constexpr int FAST_CAP = 1536;  // newline positions per tile held in shared memory (>= 16-byte lines on average)
+constexpr int WL_CAP = 188;  // newline positions per warp slice held in shared memory (>= 16.4-byte lines on average)
 
 template <int FMT>
 struct FastSmem {
     uint64_t full_bar[FAST_STAGES];
-    uint32_t warp_tot[SCAN_THREADS / 32];
-    uint32_t warp_tot_r[SCAN_THREADS / 32];
-    // newline positions of the current tile.  One buffer is enough: it is rewritten after barrier (1) of the
-    // next tile, which every thread reaches only after it has finished this tile's records.
-    uint32_t list[FAST_CAP];
-    uint32_t ghost[2][GHOSTS];  // by tile parity: [g] = g-th most recent newline before the tile
-    uint32_t rlist[FMT == SBR_FMT_FASTA ? FAST_CAP : 1];  // FASTA: list index of record starts
-    uint32_t cnt[2];    // newlines seen before the tile, by tile parity
-    uint32_t rcnt[2];   // FASTA: record starts seen before the tile
+    // per warp: [GHOSTS - 1 - g] = g-th most recent newline before the slice, [GHOSTS + i] = i-th newline of the slice
+    uint32_t wl[FAST_WARPS][GHOSTS + WL_CAP];
+    uint32_t wtot[2][FAST_WARPS];           // by tile parity: newlines | record starts << 16 of each warp slice
+    uint32_t wtail[2][FAST_WARPS][GHOSTS];  // by tile parity: the slice's last four newline positions, [0] most recent
+    uint32_t gh[2][GHOSTS];                 // by tile parity: the four most recent newlines before the tile
+    uint32_t cnt[2];                        // newlines of the region before the tile
+    uint32_t rcnt[2];                       // FASTA: record starts of the region before the tile
+    uint8_t wrl[FMT == SBR_FMT_FASTA ? FAST_WARPS : 1][FMT == SBR_FMT_FASTA ? WL_CAP + 4 : 4];  // FASTA: list index of record starts
     uint32_t first[8];  // FASTQ: the region's first eight newline positions
     uint32_t nfirst;
     uint32_t h;            // FASTQ: phase of the region's first newline
@@ -58,8 +63,8 @@ struct FastSmem {
     uint32_t fail;
     uint32_t done;         // FASTQ: the record open at the region's end has been finished
     uint32_t last_end;     // end of the last owned complete record
-    uint32_t last_start_nl, last_start_off;  // FASTA
     uint32_t crlf;
+    unsigned long long last_start;  // FASTA: (newlines up to the one before the last record start) << 32 | its offset
 };
 
 struct FastArgs {
@@ -73,6 +78,7 @@ struct FastArgs {
     uint32_t packed;
     uint32_t final_batch;
     uint32_t c7f, c0a, c80, c3e;  // byte-splat constants, passed in so that they live in registers (one LOP3 per step)
+    uint32_t code_mask, inval_mask;  // the bc_len cut of the packed scan word
     BatchHeader* hdr;
     RegionInfo* info;
     uint32_t* seg_rec_off;
@@ -100,6 +106,12 @@ __device__ __forceinline__ void eq_mask48(const uint4& v0, const uint4& v1, cons
     hi = (x4 >> 7) + (x5 << 1);
 }
 
+// store through a shared-window address kept in a register (the compiler otherwise rebuilds the window base
+// inside the compaction loops)
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // FASTQ phase detection from the first eight newlines of a region (thread 0).
 // Hypothesis h: newline 0 is the (h+1)-th line end of its record.  Under h the first record that lies
 // wholly behind a record end starts after newline s = (3 - h) & 3 and owns newlines s+1 .. s+4.
@@ -120,13 +132,16 @@ __device__ __forceinline__ bool detect_phase(const ByteSrc& B, const uint32_t* f
     return true;
 }
 
-// 2-bit pack + validity of k (<= 16) bases at tile offset s, 4 bases per step (packed mode, in-tile records)
-__device__ __forceinline__ uint64_t pack_prefix_vec(const uint8_t* sm, uint32_t s, uint32_t k) {
-    const uint32_t a = s & ~3u, sh = (s & 3u) * 8u;
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(sm + a);
+// 2-bit pack + validity of the first 4*KW bases at `tp` (any alignment; the enclosing 4-byte words are read, up to
+// 7 bytes past the window): codes | invalid << 32, cut to bc_len by the masks.
+template <int KW>
+__device__ __forceinline__ uint64_t pack_prefix_vec(const uint8_t* tp, uint32_t code_mask, uint32_t inval_mask) {
+    const uint32_t sh = ((uint32_t)(uintptr_t)tp & 3u) * 8u;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>((uintptr_t)tp & ~(uintptr_t)3);
     uint32_t codes = 0, inval = 0;
     uint32_t w = wp[0];
-    for (uint32_t j = 0; j * 4 < k; ++j) {
+#pragma unroll
+    for (int j = 0; j < KW; ++j) {
         const uint32_t wn = wp[j + 1];
         const uint32_t x = __funnelshift_r(w, wn, sh);  // four bases, base 0 in the low byte
         w = wn;
@@ -138,24 +153,25 @@ __device__ __forceinline__ uint64_t pack_prefix_vec(const uint8_t* sm, uint32_t 
         const uint32_t nz = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
         inval |= (__dp4a(nz, 0x08040201u, 0u) >> 7) << (4 * j);
     }
-    if (k < 16) { codes &= (1u << (2 * k)) - 1u; inval &= (1u << k) - 1u; }
-    return (uint64_t)codes | ((uint64_t)inval << 32);
+    return (uint64_t)(codes & code_mask) | ((uint64_t)(inval & inval_mask) << 32);
 }
 
-// owner bookkeeping of one finished FASTQ record (any path)
-template <int FMT>
-__device__ __forceinline__ void fastq_commit(const FastArgs& A, FastSmem<FMT>& S, uint32_t c, uint32_t rl, uint32_t start,
-                                             uint32_t p3, uint64_t key, uint32_t bits, uint32_t region_hi) {
-    if (bits || rl >= A.cap_r) { S.fail = 1; return; }
-    A.seg_rec_off[(size_t)c * A.cap_r + rl] = start;
-    A.seg_key[(size_t)c * A.cap_r + rl] = key;
-    if (key & KEY_NONCANON) atomicOr(&A.hdr->status, SBR_ST_NONCANONICAL);
-    atomicMax(&S.nrec, rl + 1);
-    atomicMax(&S.last_end, p3 + 1);
-    if (p3 + 1 >= region_hi) S.done = 1;
+// a record that is not in canonical form: the general evaluation (rare, kept out of line).
+// Returns the scan word with the violation bits in its top byte.
+__device__ __noinline__ uint64_t fastq_slow(const uint8_t* sm, const uint8_t* text, uint32_t lo, uint32_t hi, uint32_t nbytes,
+                                            uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t bc_len,
+                                            uint32_t packed, uint32_t first_rec) {
+    const ByteSrc B{sm, text, lo, hi};
+    uint64_t key = 0;
+    if (!(p0 < p1 && p1 < p2 && p2 < p3 && p3 < nbytes)) return (uint64_t)SBR_ST_INVALID_SEP << 56;  // positions from a failed slice
+    uint32_t bits = fastq_eval(B, p0, p1, p2, p3, bc_len, packed, key);
+    if (first_rec && B(0) != '@') bits |= SBR_ST_INVALID_START;
+    if (p3 + 1 < nbytes && B(p3 + 1) != '@') bits |= SBR_ST_INVALID_START;
+    return key | ((uint64_t)bits << 56);
 }
 
-template <int FMT>
+// KW: 32-bit words of text covering the match window (ceil(bc_len / 4), 1..4) in packed mode; 0 = unpacked keys
+template <int FMT, int KW>
 __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     uint8_t* stage_buf = dyn_smem;
@@ -175,6 +191,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
     const uint32_t region_lo = t_lo * (uint32_t)FAST_TILE;
     const uint32_t region_hi = min(t_hi * (uint32_t)FAST_TILE, A.nbytes);
     const uint32_t c7f = A.c7f, c0a = A.c0a, c80 = A.c80;
+    uint32_t* const wl = S.wl[warp];
+    const uint32_t wl_addr = smem_u32(wl + GHOSTS);  // shared-window address of the slice's entry 0
 
     auto issue = [&](int s, uint32_t tile) {  // thread 0 only
         uint32_t lo = tile * (uint32_t)FAST_TILE;
@@ -198,21 +216,27 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
         S.fail = 0;
         S.done = 0;
         S.last_end = 0;
-        S.last_start_nl = 0;
-        S.last_start_off = 0;
+        S.last_start = 0;
         S.crlf = 0;
-        for (int g = 0; g < GHOSTS; ++g) S.ghost[0][g] = NOPOS;
+        // "the newline before the region": a record whose final newline is the region's fourth starts at region_lo
+        S.gh[0][0] = region_lo - 1u;  // == NOPOS for region 0
+        for (int g = 1; g < GHOSTS; ++g) S.gh[0][g] = NOPOS;
+        // record 0 of the batch has no predecessor to check its first byte
+        if (FMT == SBR_FMT_FASTQ && c == 0 && A.text[0] != '@') S.fail = 1;
     }
+    uint32_t* const seg_off_c = A.seg_rec_off + (size_t)c * A.cap_r;
+    uint64_t* const seg_key_c = A.seg_key + (size_t)c * A.cap_r;
     __syncthreads();
     if (tid == 0)
         for (int s = 0; s < FAST_STAGES; ++s)
             if (t_lo + s < t_hi) issue(s, t_lo + s);
 
-    // Tile loop.  Two block barriers per 24 KB tile: (1) warp totals of the newline scan, (2) newline list
-    // complete.  The records of tile t are evaluated by a rotating group of warps while the other warps
-    // already build the masks of tile t+1; barrier (1) of tile t+1 doubles as "everybody is done with tile t",
-    // after which thread 0 refills tile t's stage.  Past the region's end (FASTQ only: the record left open
-    // there) the same body runs with one more barrier and on-demand loads.
+    // Tile loop, ONE block barrier per 24 KB tile.  Before it every warp has compacted the newlines of its own
+    // slice and published their number and its last four positions; after it every warp knows its place in the
+    // line cycle, fetches the four newlines before its slice and evaluates the records ending in the slice.
+    // The barrier of tile t+1 doubles as "everybody is done with tile t", after which thread 0 refills tile
+    // t's stage.  Past the region's end (FASTQ only: the record left open there) the same body runs with one
+    // more barrier and on-demand loads.
     for (uint32_t it = 0;; ++it) {
         const uint32_t tile = t_lo + it;
         if (tile >= A.ntiles) break;
@@ -231,13 +255,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
         const uint8_t* sm = stage_buf + s * FAST_TILE;
         mbar_wait(&S.full_bar[s], parity);
 
-        // ---- newline (and '>') masks of this thread's 48 bytes in each 12 KB unit -----------------------
-        const uint32_t toff = tid * SCAN_BYTES_PER_THREAD;
+        // ---- newline (and '>') masks of this lane's 48 bytes in each unit of the warp's slice ----------
+        const uint32_t woff = (uint32_t)warp * WARP_SLICE + (uint32_t)lane * SCAN_BYTES_PER_THREAD;
         uint32_t m_lo[FAST_UNITS], m_hi[FAST_UNITS], r_lo[FAST_UNITS], r_hi[FAST_UNITS];
         uint32_t cn2 = 0, cr2 = 0;  // per-unit counts, 16 bits each
 #pragma unroll
         for (int j = 0; j < FAST_UNITS; ++j) {
-            const uint32_t uoff = j * SCAN_TILE + toff;
+            const uint32_t uoff = woff + j * UNIT_BYTES;
             const uint4* src = reinterpret_cast<const uint4*>(sm + uoff);
             const uint4 v0 = src[0], v1 = src[1], v2 = src[2];
             eq_mask48(v0, v1, v2, c7f, c0a, c80, m_lo[j], m_hi[j]);
@@ -267,101 +291,117 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
             cn2 |= (uint32_t)(__popc(m_lo[j]) + __popc(m_hi[j])) << (16 * j);
         }
         const uint32_t incl_n = warp_incl_scan(cn2, lane);
-        uint32_t incl_r = 0;
-        if (FMT == SBR_FMT_FASTA) incl_r = warp_incl_scan(cr2, lane);
-        if (lane == 31) {
-            S.warp_tot[warp] = incl_n;
-            if (FMT == SBR_FMT_FASTA) S.warp_tot_r[warp] = incl_r;
+        const uint32_t tot_n = __shfl_sync(0xFFFFFFFFu, incl_n, 31);
+        const uint32_t ex_n = incl_n - cn2;
+        const uint32_t n0 = tot_n & 0xFFFFu, n_w = n0 + (tot_n >> 16);  // newlines of unit 0 / of the whole slice
+        uint32_t nr0 = 0, nr_w = 0, ex_r = 0;
+        if (FMT == SBR_FMT_FASTA) {
+            const uint32_t incl_r = warp_incl_scan(cr2, lane);
+            const uint32_t tot_r = __shfl_sync(0xFFFFFFFFu, incl_r, 31);
+            ex_r = incl_r - cr2;
+            nr0 = tot_r & 0xFFFFu;
+            nr_w = nr0 + (tot_r >> 16);
         }
-        __syncthreads();  // (1)
-        if (tid == 0 && it >= 1 && !overrun) {  // tile it-1 is finished by everybody: refill its stage
-            const uint32_t nt = tile - 1 + FAST_STAGES;
-            if (nt < t_hi) issue((it - 1) % FAST_STAGES, nt);
-        }
-        // prefix over the warps by shuffles: lane w holds warp w's totals
-        uint32_t pre_n, tot_n, pre_r = 0, tot_r = 0;
-        {
-            uint32_t t = lane < SCAN_THREADS / 32 ? S.warp_tot[lane] : 0u;
-            uint32_t inc = t;
-#pragma unroll
-            for (int d = 1; d < SCAN_THREADS / 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                if (lane >= d) inc += o;
-            }
-            pre_n = __shfl_sync(0xFFFFFFFFu, inc - t, warp);
-            tot_n = __shfl_sync(0xFFFFFFFFu, inc, SCAN_THREADS / 32 - 1);
-            if (FMT == SBR_FMT_FASTA) {
-                uint32_t tr = lane < SCAN_THREADS / 32 ? S.warp_tot_r[lane] : 0u;
-                uint32_t incr = tr;
-#pragma unroll
-                for (int d = 1; d < SCAN_THREADS / 32; d <<= 1) {
-                    uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incr, d);
-                    if (lane >= d) incr += o;
-                }
-                pre_r = __shfl_sync(0xFFFFFFFFu, incr - tr, warp);
-                tot_r = __shfl_sync(0xFFFFFFFFu, incr, SCAN_THREADS / 32 - 1);
-            }
-        }
-        // newline order inside the tile: all of unit 0, then all of unit 1
-        const uint32_t ex2 = pre_n + incl_n - cn2, exr2 = pre_r + incl_r - cr2;
-        const uint32_t T0 = tot_n & 0xFFFFu, T = T0 + (tot_n >> 16);
-        const uint32_t TR0 = tot_r & 0xFFFFu, TR = TR0 + (tot_r >> 16);
-        uint32_t* list = S.list;
-        const uint32_t* ghost = S.ghost[par];
-        // read before barrier (2): thread 0 may flip it right after that barrier, and every thread has to
-        // take the same decision about the extra barrier below
+        // read before the barrier: thread 0 may flip it right after that barrier, and every thread has to take
+        // the same decision about the extra barrier below
         const bool was_synced = S.synced != 0;
-        // ---- compact newline positions; FASTA also the list index of every record start ---------------
-        {
+        const bool fits = n_w <= (uint32_t)WL_CAP;  // warp-uniform
+
+        // ---- compact the slice's newline positions (ascending) into the warp's list ---------------------
+        if (fits) {
             bool crlf = false;
 #pragma unroll
             for (int j = 0; j < FAST_UNITS; ++j) {
-                uint32_t idx = j ? T0 + (ex2 >> 16) : (ex2 & 0xFFFFu);
-                uint32_t rk = j ? TR0 + (exr2 >> 16) : (exr2 & 0xFFFFu);
+                const uint32_t idx = j ? n0 + (ex_n >> 16) : (ex_n & 0xFFFFu);
+                uint32_t rk = j ? nr0 + (ex_r >> 16) : (ex_r & 0xFFFFu);
+                uint32_t a = wl_addr + 4u * idx;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t mm = half ? m_hi[j] : m_lo[j];
                     const uint32_t rr = half ? r_hi[j] : r_lo[j];
-                    const uint32_t o0 = j * SCAN_TILE + toff + 32 * half;
+                    const uint32_t o0 = woff + j * UNIT_BYTES + 32 * half;
+                    const uint32_t pos0 = lo + o0;
                     while (mm) {
                         const uint32_t b = __ffs(mm) - 1;
                         mm &= mm - 1;
-                        if (idx < (uint32_t)FAST_CAP) {
-                            list[idx] = lo + o0 + b;
-                            if (FMT == SBR_FMT_FASTA) {
-                                if ((rr >> b) & 1u) S.rlist[rk++] = idx;
-                                const uint32_t o = o0 + b;  // CR before LF makes a FASTA batch non-canonical
-                                crlf |= o > 0 ? sm[o - 1] == '\r' : (lo > 0 && A.text[lo - 1] == '\r');
-                            }
+                        sts_u32(a, pos0 + b);
+                        if (FMT == SBR_FMT_FASTA) {
+                            if ((rr >> b) & 1u) S.wrl[warp][rk++] = (uint8_t)((a - wl_addr) >> 2);
+                            const uint32_t o = o0 + b;  // CR before LF makes a FASTA batch non-canonical
+                            crlf |= o > 0 ? sm[o - 1] == '\r' : (lo > 0 && A.text[lo - 1] == '\r');
                         }
-                        ++idx;
+                        a += 4u;
                     }
                 }
             }
             if (FMT == SBR_FMT_FASTA && crlf) S.crlf = 1;
+        } else if (lane == 0) {
+            S.fail = 1;  // newline-dense slice: the exact scan's job
         }
-        if (tid == 0 && T > (uint32_t)FAST_CAP) S.fail = 1;  // newline-dense tile: the exact scan's job
-        __syncthreads();  // (2)
-
-        const ByteSrc B{sm, A.text, lo, lo + valid};
-        const uint32_t Tw = min(T, (uint32_t)FAST_CAP);
+        __syncwarp();
+        // ---- publish: how many, and the last four ---------------------------------------------------------
+        if (lane < GHOSTS) {
+            const uint32_t nn = fits ? n_w : 0u;
+            S.wtail[par][warp][lane] = nn > (uint32_t)lane ? wl[GHOSTS + nn - 1 - lane] : NOPOS;
+            if (lane == 0) S.wtot[par][warp] = n_w | (nr_w << 16);
+        }
+        __syncthreads();  // the tile's barrier
+        if (tid == 0 && it >= 1 && !overrun) {  // tile it-1 is finished by everybody: refill its stage
+            const uint32_t nt = tile - 1 + FAST_STAGES;
+            if (nt < t_hi) issue((it - 1) % FAST_STAGES, nt);
+        }
+        // prefix over the warp slices by shuffles: lane w holds slice w's totals (newlines | starts << 16; a tile
+        // has at most 24576 of either)
+        uint32_t pre_n, T, pre_r = 0, TR = 0;
+        {
+            const uint32_t t = lane < FAST_WARPS ? S.wtot[par][lane] : 0u;
+            uint32_t inc = t;
+#pragma unroll
+            for (int d = 1; d < FAST_WARPS; d <<= 1) {
+                uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            const uint32_t pre = __shfl_sync(0xFFFFFFFFu, inc - t, warp);
+            const uint32_t tot = __shfl_sync(0xFFFFFFFFu, inc, FAST_WARPS - 1);
+            pre_n = pre & 0xFFFFu;
+            T = tot & 0xFFFFu;
+            if (FMT == SBR_FMT_FASTA) { pre_r = pre >> 16; TR = tot >> 16; }
+        }
         const uint32_t base = S.cnt[par];
-        // ---- state of the next tile (other parity): count and the four most recent newline positions ----
-        if (tid < GHOSTS) {
-            const uint32_t g = (uint32_t)tid < Tw ? list[Tw - 1 - tid] : ghost[(uint32_t)tid - Tw];
-            S.ghost[par ^ 1u][tid] = g;
-            if (tid == 0) {
-                S.cnt[par ^ 1u] = base + T;
-                S.rcnt[par ^ 1u] = S.rcnt[par] + TR;
-                if (!overrun) S.nl_own = base + T;
+        // ---- the four newlines before the slice (lanes 0..3); warp 7 also those before the NEXT tile (4..7) --
+        if (lane < GHOSTS || (warp == FAST_WARPS - 1 && lane < 2 * GHOSTS)) {
+            const bool next_tile = lane >= GHOSTS;
+            uint32_t need = (uint32_t)lane & (GHOSTS - 1);
+            int v = (next_tile ? FAST_WARPS : warp) - 1;
+            uint32_t val;
+            while (true) {
+                if (v < 0) { val = S.gh[par][need]; break; }
+                const uint32_t cv = S.wtot[par][v] & 0xFFFFu;
+                if (need < cv) { val = S.wtail[par][v][need]; break; }
+                need -= cv;
+                --v;
+            }
+            if (!next_tile) wl[GHOSTS - 1 - lane] = val;
+            else {
+                S.gh[par ^ 1u][lane - GHOSTS] = val;
+                if (lane == GHOSTS) {
+                    S.cnt[par ^ 1u] = base + T;
+                    if (FMT == SBR_FMT_FASTA) S.rcnt[par ^ 1u] = S.rcnt[par] + TR;
+                    if (!overrun) S.nl_own = base + T;
+                }
             }
         }
+        __syncwarp();
 
         if (FMT == SBR_FMT_FASTQ) {
             if (!was_synced) {  // uniform: only the first tile(s) of a region, until eight newlines were seen
-                if (tid == 0) {
+                if (tid == 0 && !S.fail) {  // (a slice over capacity has no list to read from)
+                    const ByteSrc B{sm, A.text, lo, lo + valid};
                     uint32_t nf = S.nfirst;
-                    for (uint32_t i = 0; i < Tw && nf < 8; ++i) S.first[nf++] = list[i];
+                    for (int v = 0; v < FAST_WARPS && nf < 8; ++v) {
+                        const uint32_t nv = min(S.wtot[par][v] & 0xFFFFu, (uint32_t)WL_CAP);
+                        for (uint32_t i = 0; i < nv && nf < 8; ++i) S.first[nf++] = S.wl[v][GHOSTS + i];
+                    }
                     S.nfirst = nf;
                     if (nf >= 8) {
                         uint32_t h;
@@ -379,8 +419,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
                                 const uint32_t p0 = S.first[L - 3], p1 = S.first[L - 2], p2 = S.first[L - 1], p3 = S.first[L];
                                 uint32_t bits = fastq_eval(B, p0, p1, p2, p3, A.bc_len, A.packed, key);
                                 if (p3 + 1 < A.nbytes && B(p3 + 1) != '@') bits |= SBR_ST_INVALID_START;
-                                fastq_commit<FMT>(A, S, c, (L - fo) >> 2, (L == 3) ? region_lo : S.first[L - 4] + 1, p3, key, bits,
-                                                  region_hi);
+                                const uint32_t rl = (L - fo) >> 2;
+                                if (bits || rl >= A.cap_r) { S.fail = 1; break; }
+                                A.seg_rec_off[(size_t)c * A.cap_r + rl] = (L == 3) ? region_lo : S.first[L - 4] + 1;
+                                A.seg_key[(size_t)c * A.cap_r + rl] = key;
+                                if (key & KEY_NONCANON) atomicOr(&A.hdr->status, SBR_ST_NONCANONICAL);
+                                atomicMax(&S.nrec, rl + 1);
+                                atomicMax(&S.last_end, p3 + 1);
+                                if (p3 + 1 >= region_hi) S.done = 1;
                             }
                             S.synced = 1;
                         } else {
@@ -390,59 +436,65 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
                 }
                 __syncthreads();
             }
-            if (S.synced) {
+            if (S.synced && fits && !S.fail) {  // (S.fail: some slice of the CTA may have published nothing usable)
                 const uint32_t h = S.h, fo = S.first_owned;
-                // entries i of this tile that end a record: (h + base + i) % 4 == 3; record u -> thread (u + rot) % 256
-                const uint32_t i0 = (3u - (h + base)) & 3u;
-                const uint32_t u = ((uint32_t)tid - (it * 96u)) & (SCAN_THREADS - 1);
-                for (uint32_t i = i0 + 4u * u; i < Tw; i += 4u * SCAN_THREADS) {
-                    const uint32_t L = base + i;
+                const uint32_t L0 = base + pre_n;  // region-local index of the slice's first newline
+                // entries i of this slice that end a record: (h + L0 + i) % 4 == 3; one lane per record
+                for (uint32_t i = ((3u - (h + L0)) & 3u) + 4u * (uint32_t)lane; i < n_w; i += 128u) {
+                    const uint32_t L = L0 + i;
                     if (L < fo) continue;  // started before this region: the previous region finishes it
-                    // entry i - d of the newline stream: this tile's list, or the ghosts of earlier tiles
-                    auto nl = [&](uint32_t d) -> uint32_t { return i >= d ? list[i - d] : ghost[d - i - 1]; };
-                    const uint32_t start = (L == 3u) ? region_lo : nl(4) + 1u;
-                    if (start >= region_hi) continue;  // the next region's record (seen while running over)
-                    const uint32_t p3 = list[i], p2 = nl(1), p1 = nl(2), p0 = nl(3);
+                    const uint32_t* e = wl + GHOSTS + i;
+                    const uint32_t p3 = e[0], p2 = e[-1], p1 = e[-2], p0 = e[-3];
+                    const uint32_t start = e[-4] + 1u;  // (the ghost before region 0 is NOPOS: start 0)
+                    if (start >= region_hi) continue;   // the next region's record (seen while running over)
+                    // canonical record (LF ends, bare '+', equal lengths, long enough, next record's '@'): five byte
+                    // probes from the staged tile, or from the batch text (L2) when the record began in the previous
+                    // tile; anything else goes through the general evaluation
+                    const uint32_t seq_len = p1 - p0 - 1;
+                    bool canon = (p2 == p1 + 2) & (seq_len == p3 - p2 - 1) & (seq_len >= A.bc_len) & (p0 > start);
+                    const bool staged = (start >= lo) & (p3 + 1 < lo + valid);
+                    const uint8_t* tp0 = (staged ? sm - lo : A.text) + p0;
                     uint64_t key = 0;
                     uint32_t bits = 0;
-                    const bool first_rec = (L == 3u && c == 0);  // record 0 of the batch also checks byte 0
-                    const bool inside = p0 > lo && p3 + 1 < lo + valid;
-                    // canonical record (LF ends, bare '+', equal lengths, long enough, next record's '@'):
-                    // six byte probes; anything else goes through the general evaluation
-                    const uint32_t seq_len = p1 - p0 - 1;
-                    bool canon = p2 == p1 + 2 && seq_len == p3 - p2 - 1 && seq_len >= A.bc_len && p0 > 0;
                     if (canon) {
-                        if (inside) {  // five independent probes, combined without short-circuit branches
-                            const uint8_t* t = sm - lo;
-                            const uint32_t b0 = t[p0 - 1], b1 = t[p1 - 1], b3 = t[p3 - 1], bp = t[p1 + 1], bn = t[p3 + 1];
-                            canon = (b0 != '\r') & (b1 != '\r') & (b3 != '\r') & (bp == '+') & (bn == '@');
-                        } else {
-                            canon = B(p0 - 1) != '\r' && B(p1 - 1) != '\r' && B(p3 - 1) != '\r' && B(p1 + 1) == '+' &&
-                                    (p3 + 1 >= A.nbytes || B(p3 + 1) == '@');
-                        }
-                        if (first_rec) canon = canon && A.text[0] == '@';
+                        const uint8_t* tp1 = tp0 + (p1 - p0);
+                        const uint8_t* tp3 = tp0 + (p3 - p0);
+                        const uint32_t b0 = tp0[-1], b1 = tp1[-1], bp = tp1[1], b3 = tp3[-1];
+                        const uint32_t bn = (p3 + 1 < A.nbytes) ? tp3[1] : (uint32_t)'@';
+                        canon = (b0 != '\r') & (b1 != '\r') & (b3 != '\r') & (bp == '+') & (bn == '@');
                     }
                     if (canon) {
-                        if (!A.packed) key = (uint64_t)(p0 + 1);
-                        else if (p0 + 1 >= lo) key = pack_prefix_vec(sm, p0 + 1 - lo, A.bc_len);  // p1 < lo + valid here
-                        else key = pack_prefix(B, p0 + 1, A.bc_len);
+                        key = KW ? pack_prefix_vec<(KW ? KW : 1)>(tp0 + 1, A.code_mask, A.inval_mask) : (uint64_t)(p0 + 1);
                     } else {
-                        bits = fastq_eval(B, p0, p1, p2, p3, A.bc_len, A.packed, key);
-                        if (first_rec && B(0) != '@') bits |= SBR_ST_INVALID_START;
-                        if (p3 + 1 < A.nbytes && B(p3 + 1) != '@') bits |= SBR_ST_INVALID_START;
+                        key = fastq_slow(sm, A.text, lo, lo + valid, A.nbytes, p0, p1, p2, p3, A.bc_len, A.packed,
+                                         (L == 3u && c == 0) ? 1u : 0u);
+                        bits = (uint32_t)(key >> 56);
+                        key &= (1ull << 56) - 1ull;
+                        if (key & KEY_NONCANON) atomicOr(&A.hdr->status, SBR_ST_NONCANONICAL);
                     }
-                    fastq_commit<FMT>(A, S, c, (L - fo) >> 2, start, p3, key, bits, region_hi);
+                    const uint32_t rl = (L - fo) >> 2;
+                    if (bits || rl >= A.cap_r) { S.fail = 1; continue; }
+                    seg_off_c[rl] = start;
+                    seg_key_c[rl] = key;
+                    // records are committed in ascending order: the last one of the slice (or the one that closes the
+                    // region) carries the slice's maxima to the CTA
+                    const bool closes = p3 + 1 >= region_hi;
+                    if (i + 4u >= n_w || closes) {
+                        atomicMax(&S.nrec, rl + 1);
+                        atomicMax(&S.last_end, p3 + 1);
+                        if (closes) S.done = 1;
+                    }
                 }
             }
         } else {
-            // ---- FASTA: thread u handles the u-th record start of the tile --------------------------
-            const uint32_t rbase = S.rcnt[par];  // starts seen before this tile (record 0 of the batch not counted)
+            // ---- FASTA: lane u handles the u-th record start of the slice ------------------------------
+            const ByteSrc B{sm, A.text, lo, lo + valid};
+            const uint32_t rbase = S.rcnt[par] + pre_r;  // starts seen before this slice (record 0 of the batch not counted)
             const uint32_t own_first = (c == 0) ? 1u : 0u;
-            const uint32_t u0 = ((uint32_t)tid - (it * 96u)) & (SCAN_THREADS - 1);
-            for (uint32_t u = u0; u < TR && T <= (uint32_t)FAST_CAP; u += SCAN_THREADS) {  // dense tiles already failed
-                const uint32_t idx = S.rlist[u];
-                const uint32_t p = list[idx];
-                const uint32_t hint = (idx + 1 < Tw) ? list[idx + 1] : NOPOS;
+            for (uint32_t u = (uint32_t)lane; u < nr_w && fits; u += 32u) {  // dense slices already failed
+                const uint32_t idx = S.wrl[warp][u];
+                const uint32_t p = wl[GHOSTS + idx];
+                const uint32_t hint = (idx + 1 < n_w) ? wl[GHOSTS + idx + 1] : NOPOS;
                 uint64_t key;
                 const uint32_t why = fasta_eval(B, A.nbytes, p + 1, hint, A.bc_len, A.packed, key);
                 const uint32_t rl = rbase + u + own_first;
@@ -452,15 +504,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
                     A.seg_rec_off[(size_t)c * A.cap_r + rl] = p + 1;
                     A.seg_key[(size_t)c * A.cap_r + rl] = key;
                 }
-                if (u == TR - 1) {
-                    S.last_start_nl = base + idx + 1;
-                    S.last_start_off = p + 1;
-                }
+                if (u == nr_w - 1)
+                    atomicMax(&S.last_start, ((unsigned long long)(base + pre_n + idx + 1) << 32) | (unsigned long long)(p + 1));
             }
             if (tid == 0 && c == 0 && it == 0) {
                 uint64_t key;
                 if (B(0) != '>') S.fail = 1;
-                const uint32_t why = fasta_eval(B, A.nbytes, 0u, Tw > 0 ? list[0] : NOPOS, A.bc_len, A.packed, key);
+                const uint32_t why = fasta_eval(B, A.nbytes, 0u, (fits && n_w > 0) ? wl[GHOSTS] : NOPOS, A.bc_len, A.packed, key);
                 if (why == 1 || (why == 2 && A.final_batch)) S.fail = 1;
                 A.seg_rec_off[0] = 0;
                 A.seg_key[0] = key;
@@ -476,8 +526,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
         e.nrec = (FMT == SBR_FMT_FASTA) ? S.rcnt[n_it & 1u] + (c == 0 ? 1u : 0u) : S.nrec;
         e.phase = (FMT == SBR_FMT_FASTQ && S.synced) ? S.h : PHASE_UNKNOWN;
         e.flags = S.fail ? 1u : 0u;
-        e.last_start_nl = S.last_start_nl;
-        e.last_start_off = S.last_start_off;
+        e.last_start_nl = (uint32_t)(S.last_start >> 32);
+        e.last_start_off = (uint32_t)S.last_start;
         e.pad[0] = e.pad[1] = 0;
         A.info[c] = e;
         if (S.last_end) atomicMax(&A.hdr->consumed, S.last_end);
@@ -490,7 +540,6 @@ template <int FMT>
 __global__ void __launch_bounds__(MAX_REGIONS) k_scan_finish(BatchHeader* hdr, RegionInfo* info, uint32_t n_regions,
                                                             uint32_t nbytes, uint32_t max_records, uint32_t final_batch,
                                                             uint32_t* region_base /* [n_regions+1] */,
-                                                            const uint32_t* seg_rec_off, uint32_t cap_r,
                                                             uint32_t* rec_off_dense) {
     __shared__ uint32_t s_nl[MAX_REGIONS], s_rec[MAX_REGIONS];
     __shared__ uint32_t s_fail, s_last_region;
@@ -537,10 +586,7 @@ __global__ void __launch_bounds__(MAX_REGIONS) k_scan_finish(BatchHeader* hdr, R
     if (total_rec > max_records) s_fail = 1;
     __syncthreads();
     const bool fail = s_fail != 0;
-    if (c < n_regions) {
-        uint32_t rb = rec_before;
-        region_base[c] = rb;
-    }
+    if (c < n_regions) region_base[c] = rec_before;
     if (c == 0) {
         region_base[n_regions] = total_rec;
         if (fail) {  // hand the batch to the exact scan with a clean header
@@ -563,13 +609,6 @@ __global__ void __launch_bounds__(MAX_REGIONS) k_scan_finish(BatchHeader* hdr, R
             if (FMT == SBR_FMT_FASTA && nl_kept != 2u * total_rec) atomicOr(&hdr->status, SBR_ST_NONCANONICAL);
         }
     }
-    // FASTA, non-final: the dropped last record must not count for its region
-    if (FMT == SBR_FMT_FASTA && !final_batch && !fail && c == s_last_region) {
-        // region_base is an exclusive prefix: only entries after the last region would change, and
-        // there are no records there; the total above already excludes the dropped record
-    }
-    (void)seg_rec_off;
-    (void)cap_r;
 }
 
 }  // namespace
@@ -579,20 +618,39 @@ size_t scan_fast_smem_bytes(uint32_t fmt) {
            (fmt == SBR_FMT_FASTA ? sizeof(FastSmem<SBR_FMT_FASTA>) : sizeof(FastSmem<SBR_FMT_FASTQ>));
 }
 
+using FastKernel = void (*)(FastArgs);
+// FASTQ kernels are specialised on the number of text words covering the match window
+static FastKernel fastq_kernel(uint32_t bc_len, uint32_t packed) {
+    if (!packed) return k_scan_fast<SBR_FMT_FASTQ, 0>;
+    switch ((bc_len + 3) / 4) {
+        case 1: return k_scan_fast<SBR_FMT_FASTQ, 1>;
+        case 2: return k_scan_fast<SBR_FMT_FASTQ, 2>;
+        case 3: return k_scan_fast<SBR_FMT_FASTQ, 3>;
+        default: return k_scan_fast<SBR_FMT_FASTQ, 4>;
+    }
+}
+
 cudaError_t scan_fast_prepare(int device, int* grid_fastq, int* grid_fasta) {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_scan_fast<SBR_FMT_FASTQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)scan_fast_smem_bytes(SBR_FMT_FASTQ))) != cudaSuccess)
-        return e;
-    if ((e = cudaFuncSetAttribute(k_scan_fast<SBR_FMT_FASTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const FastKernel all[] = {k_scan_fast<SBR_FMT_FASTQ, 0>, k_scan_fast<SBR_FMT_FASTQ, 1>, k_scan_fast<SBR_FMT_FASTQ, 2>,
+                              k_scan_fast<SBR_FMT_FASTQ, 3>, k_scan_fast<SBR_FMT_FASTQ, 4>};
+    for (FastKernel k : all)
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)scan_fast_smem_bytes(SBR_FMT_FASTQ))) != cudaSuccess)
+            return e;
+    if ((e = cudaFuncSetAttribute(k_scan_fast<SBR_FMT_FASTA, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)scan_fast_smem_bytes(SBR_FMT_FASTA))) != cudaSuccess)
         return e;
-    int sms = 0, q = 0, a = 0;
+    int sms = 0, q = 1 << 30, a = 0;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_scan_fast<SBR_FMT_FASTQ>, SCAN_THREADS,
-                                                           scan_fast_smem_bytes(SBR_FMT_FASTQ))) != cudaSuccess)
-        return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_scan_fast<SBR_FMT_FASTA>, SCAN_THREADS,
+    for (FastKernel k : all) {  // one grid for every FASTQ variant: the smallest residency
+        int qq = 0;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&qq, k, SCAN_THREADS, scan_fast_smem_bytes(SBR_FMT_FASTQ))) !=
+            cudaSuccess)
+            return e;
+        q = qq < q ? qq : q;
+    }
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_scan_fast<SBR_FMT_FASTA, 0>, SCAN_THREADS,
                                                            scan_fast_smem_bytes(SBR_FMT_FASTA))) != cudaSuccess)
         return e;
     q = (q < 1 ? 1 : q) * sms;
@@ -635,19 +693,21 @@ cudaError_t scan_fast_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbyte
     A.c0a = 0x0A0A0A0Au;
     A.c80 = 0x80808080u;
     A.c3e = 0x3E3E3E3Eu;
+    A.code_mask = bc_len >= 16 ? 0xFFFFFFFFu : ((1u << (2 * bc_len)) - 1u);
+    A.inval_mask = bc_len >= 16 ? 0xFFFFu : ((1u << bc_len) - 1u);
     A.hdr = hdr;
     A.info = info;
     A.seg_rec_off = seg_rec_off;
     A.seg_key = seg_key;
     size_t smem = scan_fast_smem_bytes(fmt);
     if (fmt == SBR_FMT_FASTQ) {
-        k_scan_fast<SBR_FMT_FASTQ><<<n_regions, SCAN_THREADS, smem, stream>>>(A);
+        fastq_kernel(bc_len, packed)<<<n_regions, SCAN_THREADS, smem, stream>>>(A);
         k_scan_finish<SBR_FMT_FASTQ><<<1, MAX_REGIONS, 0, stream>>>(hdr, info, n_regions, nbytes, max_records, final_batch,
-                                                                    region_base, seg_rec_off, cap_r, rec_off_dense);
+                                                                    region_base, rec_off_dense);
     } else {
-        k_scan_fast<SBR_FMT_FASTA><<<n_regions, SCAN_THREADS, smem, stream>>>(A);
+        k_scan_fast<SBR_FMT_FASTA, 0><<<n_regions, SCAN_THREADS, smem, stream>>>(A);
         k_scan_finish<SBR_FMT_FASTA><<<1, MAX_REGIONS, 0, stream>>>(hdr, info, n_regions, nbytes, max_records, final_batch,
-                                                                    region_base, seg_rec_off, cap_r, rec_off_dense);
+                                                                    region_base, rec_off_dense);
     }
     return cudaGetLastError();
 }

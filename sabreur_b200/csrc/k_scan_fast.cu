@@ -26,6 +26,8 @@
 //   * per record: validate ('+' line, equal lengths, CR, next record's '@'), 2-bit pack the first bc_len
 //     bases, write seg_rec_off / seg_key at the region-local index.  The match kernel compacts the
 //     per-region segments into dense arrays while it reads the keys.
+#include <cstdlib>
+
 #include "scan_common.cuh"
 
 namespace sbr {
@@ -40,6 +42,10 @@ constexpr int UNIT_BYTES = 32 * SCAN_BYTES_PER_THREAD;  // 1536 B: one 48-byte c
 constexpr int WARP_SLICE = FAST_UNITS * UNIT_BYTES;     // 3072 B
 constexpr int FAST_TILE = FAST_WARPS * WARP_SLICE;      // 24 KB
 constexpr int FAST_STAGES = 2;
+// every stage is preceded by a copy of the last TAIL_PAD bytes of the previous tile, so that a record which began there is
+// still addressable in shared memory at (stage base + position - tile start)
+constexpr int TAIL_PAD = 512;
+__host__ __device__ constexpr int stage_stride(int fmt) { return (fmt == SBR_FMT_FASTQ ? TAIL_PAD : 0) + FAST_TILE; }  // FASTA has no use for the pad
 constexpr int WL_CAP = 188;  // newline positions per warp slice held in shared memory (>= 16.4-byte lines on average)
 
 template <int FMT>
@@ -59,10 +65,9 @@ struct FastSmem {
     uint32_t synced;
     uint32_t first_owned;  // FASTQ: region-local index of the final newline of the first owned record
     uint32_t nl_own;       // newlines inside the region's own byte range
-    uint32_t nrec;
+    uint32_t wmax[FAST_WARPS][2];  // FASTQ: per warp {records owned so far, end of the last one}
     uint32_t fail;
     uint32_t done;         // FASTQ: the record open at the region's end has been finished
-    uint32_t last_end;     // end of the last owned complete record
     uint32_t crlf;
     unsigned long long last_start;  // FASTA: (newlines up to the one before the last record start) << 32 | its offset
 };
@@ -112,6 +117,17 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 // FASTQ phase detection from the first eight newlines of a region (thread 0).
 // Hypothesis h: newline 0 is the (h+1)-th line end of its record.  Under h the first record that lies
 // wholly behind a record end starts after newline s = (3 - h) & 3 and owns newlines s+1 .. s+4.
@@ -132,17 +148,16 @@ __device__ __forceinline__ bool detect_phase(const ByteSrc& B, const uint32_t* f
     return true;
 }
 
-// 2-bit pack + validity of the first 4*KW bases at `tp` (any alignment; the enclosing 4-byte words are read, up to
-// 7 bytes past the window): codes | invalid << 32, cut to bc_len by the masks.
+// 2-bit pack + validity of the first 4*KW bases at shared-window address `addr` (any alignment; the enclosing 4-byte
+// words are read, up to 7 bytes past the window): codes | invalid << 32, cut to bc_len by the masks.
 template <int KW>
-__device__ __forceinline__ uint64_t pack_prefix_vec(const uint8_t* tp, uint32_t code_mask, uint32_t inval_mask) {
-    const uint32_t sh = ((uint32_t)(uintptr_t)tp & 3u) * 8u;
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>((uintptr_t)tp & ~(uintptr_t)3);
+__device__ __forceinline__ uint64_t pack_prefix_vec(uint32_t addr, uint32_t code_mask, uint32_t inval_mask) {
+    const uint32_t sh = (addr & 3u) * 8u, wa = addr & ~3u;
     uint32_t codes = 0, inval = 0;
-    uint32_t w = wp[0];
+    uint32_t w = lds_u32(wa);
 #pragma unroll
     for (int j = 0; j < KW; ++j) {
-        const uint32_t wn = wp[j + 1];
+        const uint32_t wn = lds_u32(wa + 4u * (j + 1));
         const uint32_t x = __funnelshift_r(w, wn, sh);  // four bases, base 0 in the low byte
         w = wn;
         const uint32_t c = (x >> 1) & 0x03030303u;      // code = (ascii >> 1) & 3
@@ -174,8 +189,9 @@ __device__ __noinline__ uint64_t fastq_slow(const uint8_t* sm, const uint8_t* te
 template <int FMT, int KW>
 __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
-    uint8_t* stage_buf = dyn_smem;
-    FastSmem<FMT>& S = *reinterpret_cast<FastSmem<FMT>*>(dyn_smem + FAST_STAGES * FAST_TILE);
+    constexpr int STAGE_STRIDE = stage_stride(FMT);
+    uint8_t* stage_buf = dyn_smem + (STAGE_STRIDE - FAST_TILE);  // stage s = stage_buf + s * STAGE_STRIDE, its tail pad right before it
+    FastSmem<FMT>& S = *reinterpret_cast<FastSmem<FMT>*>(dyn_smem + FAST_STAGES * STAGE_STRIDE);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t c = blockIdx.x;
     // A.ntiles / tiles_per_region count FAST_TILE-sized tiles
@@ -199,7 +215,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
         uint32_t valid = min((uint32_t)FAST_TILE, A.nbytes - lo);
         uint32_t bytes = (valid + 15u) & ~15u;  // the text buffer is padded to 16 bytes
         mbar_expect_tx(&S.full_bar[s], bytes);
-        bulk_g2s(stage_buf + s * FAST_TILE, A.text + lo, bytes, &S.full_bar[s]);
+        bulk_g2s(stage_buf + s * STAGE_STRIDE, A.text + lo, bytes, &S.full_bar[s]);
     };
 
     if (tid == 0) {
@@ -212,10 +228,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
         S.cnt[0] = S.cnt[1] = 0;
         S.rcnt[0] = S.rcnt[1] = 0;
         S.nl_own = 0;
-        S.nrec = 0;
+        for (int w = 0; w < FAST_WARPS; ++w) S.wmax[w][0] = S.wmax[w][1] = 0;
         S.fail = 0;
         S.done = 0;
-        S.last_end = 0;
         S.last_start = 0;
         S.crlf = 0;
         // "the newline before the region": a record whose final newline is the region's fourth starts at region_lo
@@ -252,7 +267,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
         if (overrun && tid == 0) issue(s, tile);  // on demand: one extra tile per region, rarely more
         const uint32_t lo = tile * (uint32_t)FAST_TILE;
         const uint32_t valid = min((uint32_t)FAST_TILE, A.nbytes - lo);
-        const uint8_t* sm = stage_buf + s * FAST_TILE;
+        const uint8_t* sm = stage_buf + s * STAGE_STRIDE;
         mbar_wait(&S.full_bar[s], parity);
 
         // ---- newline (and '>') masks of this lane's 48 bytes in each unit of the warp's slice ----------
@@ -350,6 +365,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
             const uint32_t nt = tile - 1 + FAST_STAGES;
             if (nt < t_hi) issue((it - 1) % FAST_STAGES, nt);
         }
+        if (FMT == SBR_FMT_FASTQ && warp == FAST_WARPS - 2) {  // the tile's last TAIL_PAD bytes -> the pad in front of the other stage (the next tile)
+            const uint4 v = *reinterpret_cast<const uint4*>(sm + FAST_TILE - TAIL_PAD + 16 * lane);
+            *reinterpret_cast<uint4*>(stage_buf + (s ^ 1) * STAGE_STRIDE - TAIL_PAD + 16 * lane) = v;
+        }
         // prefix over the warp slices by shuffles: lane w holds slice w's totals (newlines | starts << 16; a tile
         // has at most 24576 of either)
         uint32_t pre_n, T, pre_r = 0, TR = 0;
@@ -424,8 +443,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
                                 A.seg_rec_off[(size_t)c * A.cap_r + rl] = (L == 3) ? region_lo : S.first[L - 4] + 1;
                                 A.seg_key[(size_t)c * A.cap_r + rl] = key;
                                 if (key & KEY_NONCANON) atomicOr(&A.hdr->status, SBR_ST_NONCANONICAL);
-                                atomicMax(&S.nrec, rl + 1);
-                                atomicMax(&S.last_end, p3 + 1);
+                                S.wmax[0][0] = rl + 1;  // ascending: any record of warp 0's slices comes later
+                                S.wmax[0][1] = p3 + 1;
                                 if (p3 + 1 >= region_hi) S.done = 1;
                             }
                             S.synced = 1;
@@ -439,50 +458,76 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
             if (S.synced && fits && !S.fail) {  // (S.fail: some slice of the CTA may have published nothing usable)
                 const uint32_t h = S.h, fo = S.first_owned;
                 const uint32_t L0 = base + pre_n;  // region-local index of the slice's first newline
-                // entries i of this slice that end a record: (h + L0 + i) % 4 == 3; one lane per record
-                for (uint32_t i = ((3u - (h + L0)) & 3u) + 4u * (uint32_t)lane; i < n_w; i += 128u) {
+                // entries i of this slice that end a record: (h + L0 + i) % 4 == 3.  TWO lanes per record (a 3 KB
+                // slice ends about ten 150-bp records: one lane each would leave the warp two thirds idle): the even
+                // lane probes around the header's and the record's final newline and packs the first half of the
+                // match window, the odd lane probes around the sequence's newline and packs the second half; one
+                // shuffle pair merges them and the even lane commits.  The loop bounds are warp-uniform so that the
+                // shuffles run converged.
+                constexpr int WPL = KW > 2 ? 2 : 1;  // text words packed per lane
+                const uint32_t role = (uint32_t)lane & 1u;
+                const uint32_t sbase = smem_u32(sm) - lo;  // shared-window address of batch position 0 (wraps)
+                for (uint32_t ib = (3u - (h + L0)) & 3u; ib < n_w; ib += 64u) {
+                    const uint32_t i = ib + 4u * ((uint32_t)lane >> 1);
+                    uint32_t p3 = 0, p2 = 0, p1 = 0, p0 = 0, start = 0;
+                    bool act = i < n_w;
+                    if (act) {
+                        const uint32_t* e = wl + GHOSTS + i;
+                        p3 = e[0]; p2 = e[-1]; p1 = e[-2]; p0 = e[-3];
+                        start = e[-4] + 1u;  // (the ghost before region 0 is NOPOS: start 0)
+                    }
                     const uint32_t L = L0 + i;
-                    if (L < fo) continue;  // started before this region: the previous region finishes it
-                    const uint32_t* e = wl + GHOSTS + i;
-                    const uint32_t p3 = e[0], p2 = e[-1], p1 = e[-2], p0 = e[-3];
-                    const uint32_t start = e[-4] + 1u;  // (the ghost before region 0 is NOPOS: start 0)
-                    if (start >= region_hi) continue;   // the next region's record (seen while running over)
-                    // canonical record (LF ends, bare '+', equal lengths, long enough, next record's '@'): five byte
-                    // probes from the staged tile, or from the batch text (L2) when the record began in the previous
-                    // tile; anything else goes through the general evaluation
+                    // L < fo: started before this region, the previous region finishes it; start >= region_hi: the
+                    // next region's record (seen while running over)
+                    act = act & (L >= fo) & (start < region_hi);
+                    // canonical record (LF ends, bare '+', equal lengths, long enough, next record's '@'): byte probes
+                    // from the staged tile, or from the batch text (L2) when the record began in the previous tile;
+                    // anything else goes through the general evaluation
                     const uint32_t seq_len = p1 - p0 - 1;
-                    bool canon = (p2 == p1 + 2) & (seq_len == p3 - p2 - 1) & (seq_len >= A.bc_len) & (p0 > start);
-                    const bool staged = (start >= lo) & (p3 + 1 < lo + valid);
-                    const uint8_t* tp0 = (staged ? sm - lo : A.text) + p0;
-                    uint64_t key = 0;
-                    uint32_t bits = 0;
-                    if (canon) {
-                        const uint8_t* tp1 = tp0 + (p1 - p0);
-                        const uint8_t* tp3 = tp0 + (p3 - p0);
-                        const uint32_t b0 = tp0[-1], b1 = tp1[-1], bp = tp1[1], b3 = tp3[-1];
-                        const uint32_t bn = (p3 + 1 < A.nbytes) ? tp3[1] : (uint32_t)'@';
-                        canon = (b0 != '\r') & (b1 != '\r') & (b3 != '\r') & (bp == '+') & (bn == '@');
+                    const bool shape = act & (p2 == p1 + 2) & (seq_len == p3 - p2 - 1) & (seq_len >= A.bc_len) & (p0 > start);
+                    uint32_t codes = 0, iv_ok = 0;
+                    if (shape && (start + TAIL_PAD >= lo) & (p3 + 1 < lo + valid)) {  // all of it is staged (tail pad included)
+                        const uint32_t qa = role ? p1 : p0, qb = role ? p1 : p3;
+                        const uint32_t x = lds_u8(sbase + qa - 1), y = lds_u8(sbase + qb - 1), z = lds_u8(sbase + qb + 1);
+                        const uint32_t zc = role ? (uint32_t)'+' : (uint32_t)'@';
+                        const uint32_t ok = (x != '\r') & (y != '\r') & (z == zc);
+                        if (KW) {
+                            const uint64_t pk = pack_prefix_vec<WPL>(sbase + p0 + 1 + 4 * WPL * role, 0xFFFFFFFFu, 0xFFFFu);
+                            codes = (uint32_t)pk;
+                            iv_ok = (uint32_t)(pk >> 32);
+                        }
+                        iv_ok |= ok << 16;
                     }
-                    if (canon) {
-                        key = KW ? pack_prefix_vec<(KW ? KW : 1)>(tp0 + 1, A.code_mask, A.inval_mask) : (uint64_t)(p0 + 1);
-                    } else {
-                        key = fastq_slow(sm, A.text, lo, lo + valid, A.nbytes, p0, p1, p2, p3, A.bc_len, A.packed,
-                                         (L == 3u && c == 0) ? 1u : 0u);
-                        bits = (uint32_t)(key >> 56);
-                        key &= (1ull << 56) - 1ull;
-                        if (key & KEY_NONCANON) atomicOr(&A.hdr->status, SBR_ST_NONCANONICAL);
-                    }
-                    const uint32_t rl = (L - fo) >> 2;
-                    if (bits || rl >= A.cap_r) { S.fail = 1; continue; }
-                    seg_off_c[rl] = start;
-                    seg_key_c[rl] = key;
-                    // records are committed in ascending order: the last one of the slice (or the one that closes the
-                    // region) carries the slice's maxima to the CTA
-                    const bool closes = p3 + 1 >= region_hi;
-                    if (i + 4u >= n_w || closes) {
-                        atomicMax(&S.nrec, rl + 1);
-                        atomicMax(&S.last_end, p3 + 1);
-                        if (closes) S.done = 1;
+                    const uint32_t codes_o = __shfl_xor_sync(0xFFFFFFFFu, codes, 1);
+                    const uint32_t ivok_o = __shfl_xor_sync(0xFFFFFFFFu, iv_ok, 1);
+                    if (act && role == 0) {
+                        uint64_t key;
+                        uint32_t bits = 0;
+                        if ((iv_ok & ivok_o) >> 16) {  // shape and probes hold on both lanes
+                            const uint32_t cc = (codes | (codes_o << (8 * WPL))) & A.code_mask;
+                            const uint32_t iv = ((iv_ok & 0xFFFFu) | ((ivok_o & 0xFFFFu) << (4 * WPL))) & A.inval_mask;
+                            key = KW ? ((uint64_t)cc | ((uint64_t)iv << 32)) : (uint64_t)(p0 + 1);
+                        } else {
+                            key = fastq_slow(sm, A.text, lo, lo + valid, A.nbytes, p0, p1, p2, p3, A.bc_len, A.packed,
+                                             (L == 3u && c == 0) ? 1u : 0u);
+                            bits = (uint32_t)(key >> 56);
+                            key &= (1ull << 56) - 1ull;
+                            if (key & KEY_NONCANON) atomicOr(&A.hdr->status, SBR_ST_NONCANONICAL);
+                        }
+                        const uint32_t rl = (L - fo) >> 2;
+                        if (bits || rl >= A.cap_r) S.fail = 1;
+                        else {
+                            seg_off_c[rl] = start;
+                            seg_key_c[rl] = key;
+                            // records are committed in ascending order: the last one of the slice (or the one that
+                            // closes the region) carries the slice's maxima to the CTA
+                            const bool closes = p3 + 1 >= region_hi;
+                            if (i + 4u >= n_w || closes) {
+                                S.wmax[warp][0] = rl + 1;
+                                S.wmax[warp][1] = p3 + 1;
+                                if (closes) S.done = 1;
+                            }
+                        }
                     }
                 }
             }
@@ -523,14 +568,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
         const uint32_t n_it = t_hi - t_lo;  // own tiles processed: the final counts sit in parity n_it & 1
         RegionInfo e;
         e.nl_own = S.nl_own;
-        e.nrec = (FMT == SBR_FMT_FASTA) ? S.rcnt[n_it & 1u] + (c == 0 ? 1u : 0u) : S.nrec;
+        uint32_t nrec = 0, last_end = 0;
+        for (int w = 0; w < FAST_WARPS; ++w) { nrec = max(nrec, S.wmax[w][0]); last_end = max(last_end, S.wmax[w][1]); }
+        e.nrec = (FMT == SBR_FMT_FASTA) ? S.rcnt[n_it & 1u] + (c == 0 ? 1u : 0u) : nrec;
         e.phase = (FMT == SBR_FMT_FASTQ && S.synced) ? S.h : PHASE_UNKNOWN;
         e.flags = S.fail ? 1u : 0u;
         e.last_start_nl = (uint32_t)(S.last_start >> 32);
         e.last_start_off = (uint32_t)S.last_start;
         e.pad[0] = e.pad[1] = 0;
         A.info[c] = e;
-        if (S.last_end) atomicMax(&A.hdr->consumed, S.last_end);
+        if (last_end) atomicMax(&A.hdr->consumed, last_end);
         if (S.crlf) atomicOr(&A.hdr->status, SBR_ST_NONCANONICAL);
     }
 }
@@ -614,7 +661,8 @@ __global__ void __launch_bounds__(MAX_REGIONS) k_scan_finish(BatchHeader* hdr, R
 }  // namespace
 
 size_t scan_fast_smem_bytes(uint32_t fmt) {
-    return (size_t)FAST_STAGES * FAST_TILE +
+    static const size_t pad = getenv("SBR_SCAN_PAD_SMEM") ? (size_t)atoi(getenv("SBR_SCAN_PAD_SMEM")) : 0;  // occupancy experiments
+    return pad + (size_t)FAST_STAGES * stage_stride((int)fmt) +
            (fmt == SBR_FMT_FASTA ? sizeof(FastSmem<SBR_FMT_FASTA>) : sizeof(FastSmem<SBR_FMT_FASTQ>));
 }
 

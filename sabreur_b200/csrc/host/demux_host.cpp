@@ -1,0 +1,561 @@
+// demux_host.cpp -- host pipeline around the C ABI: decompress -> pinned slots -> GPU(s) -> per-barcode writers.
+//
+//   reader thread   decompresses the input into pinned slot buffers (sbr_slot_buffer) and cuts batches at a GUESSED
+//                   record boundary so that several batches can be in flight on several GPUs at once;
+//   GPU thread      the caller's thread: submits batches round-robin (batch s -> GPU s mod G), waits for them in
+//                   sequence order and VERIFIES every guess against the scan (`consumed`): exact record boundaries
+//                   come from the GPU alone.  A wrong guess costs one re-submission of the following batch with the
+//                   unconsumed tail in front of it (every slot keeps room there);
+//   writer thread   takes results in batch order, gathers every bin's records (order[] / rec_off[]) into one
+//                   buffer per output file, compresses it as one member and appends it: files keep input order
+//                   exactly like the sequential reference (src/demux.rs:49-66, utils.rs:133-158).
+#include "demux_host.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <exception>
+#include <mutex>
+#include <thread>
+
+#include "../../../include/sabreur_gpu.h"
+
+namespace sabreur {
+
+std::vector<std::vector<std::string>> split_by_tab(const std::string& content) {
+    if (content.find('\t') == std::string::npos) throw std::runtime_error("Input string is not tab-delimited");
+    std::vector<std::vector<std::string>> rows;
+    size_t pos = 0;
+    while (pos < content.size()) {  // str::lines(): split at '\n', a trailing '\r' is dropped, no empty last line
+        size_t nl = content.find('\n', pos);
+        std::string line = content.substr(pos, nl == std::string::npos ? std::string::npos : nl - pos);
+        pos = nl == std::string::npos ? content.size() : nl + 1;
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        std::vector<std::string> f;
+        size_t a = 0;
+        while (true) {
+            size_t t = line.find('\t', a);
+            f.push_back(line.substr(a, t == std::string::npos ? std::string::npos : t - a));
+            if (t == std::string::npos) break;
+            a = t + 1;
+        }
+        rows.push_back(std::move(f));
+    }
+    return rows;
+}
+
+namespace {
+
+using Clock = std::chrono::steady_clock;
+double secs(Clock::time_point a, Clock::time_point b) { return std::chrono::duration<double>(b - a).count(); }
+
+struct Gpu {
+    sbr_ctx* ctx = nullptr;
+    std::vector<uint8_t*> slot_host;
+};
+
+struct Batch {
+    uint64_t seq = 0;
+    int gpu = 0;
+    uint32_t slot = 0;
+    uint64_t off = 0, n = 0;  // the batch is slot_host[off .. off + n)
+    bool final_batch = false;
+    sbr_result res{};
+};
+
+template <class T>
+class Channel {  // bounded by construction (every item holds a slot)
+public:
+    void push(T v) {
+        { std::lock_guard<std::mutex> l(m_); q_.push_back(std::move(v)); }
+        cv_.notify_all();
+    }
+    void close() {
+        { std::lock_guard<std::mutex> l(m_); closed_ = true; }
+        cv_.notify_all();
+    }
+    bool pop(T& out) {  // false: closed and drained
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return !q_.empty() || closed_; });
+        if (q_.empty()) return false;
+        out = std::move(q_.front());
+        q_.pop_front();
+        return true;
+    }
+    bool try_pop(T& out) {
+        std::lock_guard<std::mutex> l(m_);
+        if (q_.empty()) return false;
+        out = std::move(q_.front());
+        q_.pop_front();
+        return true;
+    }
+    bool drained() {
+        std::lock_guard<std::mutex> l(m_);
+        return closed_ && q_.empty();
+    }
+
+private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<T> q_;
+    bool closed_ = false;
+};
+
+// ---- guessed record boundary near the end of [p, p + n): the offset where the last incomplete record starts ----
+// FASTQ: a line that starts with '@' and whose second-next line starts with '+' ('@' also opens quality lines, but
+// then the second-next line is a sequence).  FASTA: the last line starting with '>'.  Only a guess: the GPU verifies.
+uint64_t guess_cut(const uint8_t* p, uint64_t n, uint32_t fmt, uint64_t window) {
+    const uint64_t lo = n > window ? n - window : 0;
+    std::vector<uint64_t> starts;  // line starts, descending
+    uint64_t e = n;
+    while (e > lo && starts.size() < 4096) {
+        const void* r = memrchr(p + lo, '\n', e - lo);
+        if (!r) break;
+        uint64_t nl = (const uint8_t*)r - p;
+        if (nl + 1 < n) starts.push_back(nl + 1);
+        e = nl;
+    }
+    if (fmt == SBR_FMT_FASTA) {
+        for (uint64_t s : starts)
+            if (p[s] == '>') return s;
+        return n;
+    }
+    for (size_t j = 2; j < starts.size(); ++j)  // starts[j-2] is two lines after starts[j]
+        if (p[starts[j]] == '@' && p[starts[j - 2]] == '+') return starts[j];
+    return n;
+}
+
+// canonical bytes of one record (needletail write_fasta / write_fastq, LineEnding::Unix; src/utils.rs:142-154)
+void canonical_record(const uint8_t* r, size_t n, uint32_t fmt, std::vector<uint8_t>& out) {
+    std::vector<std::pair<size_t, size_t>> lines;  // [begin, end) without the line end
+    size_t a = 0;
+    while (a < n) {
+        const void* q = memchr(r + a, '\n', n - a);
+        size_t e = q ? (size_t)((const uint8_t*)q - r) : n;
+        size_t le = e;
+        if (le > a && r[le - 1] == '\r') --le;
+        lines.emplace_back(a, le);
+        a = e + 1;
+    }
+    auto put = [&](size_t b, size_t e) { out.insert(out.end(), r + b, r + e); };
+    if (lines.empty()) return;
+    if (fmt == SBR_FMT_FASTQ) {
+        if (lines.size() < 4) { out.insert(out.end(), r, r + n); return; }
+        put(lines[0].first, lines[0].second); out.push_back('\n');
+        put(lines[1].first, lines[1].second); out.push_back('\n');
+        out.push_back('+'); out.push_back('\n');
+        put(lines[3].first, lines[3].second); out.push_back('\n');
+    } else {
+        put(lines[0].first, lines[0].second); out.push_back('\n');
+        for (size_t i = 1; i < lines.size(); ++i) put(lines[i].first, lines[i].second);
+        out.push_back('\n');
+    }
+}
+
+struct Sink {  // where the records of one bin go in this pass
+    FILE* fh = nullptr;
+    std::vector<uint8_t> raw, packed;
+    uint64_t written_records = 0;
+};
+
+class Pass {
+public:
+    Pass(const std::string& path, std::vector<FILE*> bin_files, const std::vector<std::string>& barcodes, uint8_t mismatch,
+         Format out_format, int level, const HostOptions& opt, RunStats* stats)
+        : path_(path), opt_(opt), out_format_(out_format), level_(level), stats_(stats) {
+        n_bins_ = (uint32_t)barcodes.size() + 1;
+        sinks_.resize(n_bins_);
+        for (uint32_t b = 0; b < n_bins_; ++b) sinks_[b].fh = bin_files[b];
+        const uint32_t k = (uint32_t)barcodes[0].size();  // bc_len from row 0 (demux.rs:34, refinement H2)
+        std::vector<uint8_t> tab((size_t)barcodes.size() * k, 0);
+        std::vector<uint32_t> lens(barcodes.size());
+        for (size_t i = 0; i < barcodes.size(); ++i) {
+            const size_t len = std::min<size_t>(barcodes[i].size(), k);  // zip() never looks past seq[..bc_len]
+            std::memcpy(tab.data() + i * k, barcodes[i].data(), len);
+            lens[i] = (uint32_t)len;
+        }
+        int ndev = sbr_device_count();
+        if (ndev <= 0) throw std::runtime_error(std::string("no usable GPU: ") + sbr_last_error(nullptr) + " (there is no CPU fallback)");
+        G_ = std::max(1, std::min(opt.n_gpus, ndev));
+        S_ = std::max<uint32_t>(1, opt.slots_per_gpu);
+        cap_ = opt.batch_bytes;
+        reserve_ = std::min<uint64_t>(cap_ / 8, 16ull << 20);
+        gpus_.resize(G_);
+        for (int g = 0; g < G_; ++g) {
+            sbr_config cfg{};
+            cfg.device = g; cfg.fmt = SBR_FMT_AUTO; cfg.n_barcodes = (uint32_t)barcodes.size(); cfg.bc_len = k;
+            cfg.barcodes = tab.data(); cfg.bc_lens = lens.data(); cfg.mismatch = mismatch; cfg.n_slots = S_;
+            cfg.batch_bytes = cap_; cfg.max_records = 0; cfg.flags = 0;
+            if (sbr_create(&gpus_[g].ctx, &cfg) != SBR_OK)
+                throw std::runtime_error(std::string("sbr_create failed: ") + sbr_last_error(nullptr));
+            gpus_[g].slot_host.resize(S_);
+            for (uint32_t s = 0; s < S_; ++s) {
+                uint64_t c = 0;
+                if (sbr_slot_buffer(gpus_[g].ctx, s, &gpus_[g].slot_host[s], &c) != SBR_OK)
+                    throw std::runtime_error(std::string("sbr_slot_buffer failed: ") + sbr_last_error(gpus_[g].ctx));
+            }
+        }
+    }
+    ~Pass() {
+        for (auto& g : gpus_) sbr_destroy(g.ctx);
+    }
+
+    // strict: SE semantics (`record?`, demux.rs:50: a bad record is an error); otherwise PE semantics (the loop
+    // `while let Some(Ok(record))` just stops, demux.rs:101,114).  Returns is_unk_empty.
+    bool run(bool strict, Counts& nb_records, const std::vector<std::string>& barcodes) {
+        const auto t0 = Clock::now();
+        std::thread reader([&] { reader_main(); });
+        std::thread writer([&] { writer_main(); });
+        try {
+            gpu_main();
+        } catch (...) {
+            fail(std::current_exception());
+        }
+        to_write_.close();
+        reader.join();
+        writer.join();
+        if (stats_) stats_->total_s += secs(t0, Clock::now());
+        if (error_) std::rethrow_exception(error_);
+        for (uint32_t b = 0; b + 1 < n_bins_; ++b)
+            if (sinks_[b].written_records) {
+                auto it = std::find_if(nb_records.begin(), nb_records.end(), [&](auto& p) { return p.first == barcodes[b]; });
+                if (it == nb_records.end()) nb_records.emplace_back(barcodes[b], sinks_[b].written_records);
+                else it->second += sinks_[b].written_records;
+            }
+        const bool unk_empty = sinks_[n_bins_ - 1].written_records == 0;
+        if (bad_flags_) {
+            char msg[160];
+            snprintf(msg, sizeof msg, "record %llu: %s%s%s%s%s", (unsigned long long)bad_record_,
+                     (bad_flags_ & SBR_ST_INVALID_START) ? "invalid start byte " : "",
+                     (bad_flags_ & SBR_ST_INVALID_SEP) ? "invalid separator line " : "",
+                     (bad_flags_ & SBR_ST_UNEQUAL_LEN) ? "sequence and quality lengths differ " : "",
+                     (bad_flags_ & SBR_ST_SHORT_READ) ? "read shorter than the barcode " : "",
+                     (bad_flags_ & SBR_ST_TRUNCATED) ? "truncated record" : "");
+            if (bad_flags_ & SBR_ST_SHORT_READ) throw ShortReadPanic(msg);
+            if (strict) throw ParseError(msg);
+        }
+        return unk_empty;
+    }
+
+private:
+    void fail(std::exception_ptr e) {
+        {
+            std::lock_guard<std::mutex> l(err_m_);
+            if (!error_) error_ = e;
+        }
+        stop_.store(true);
+        slot_cv_.notify_all();
+        filled_.close();
+        to_write_.close();
+    }
+
+    // ---- reader: decompress into the next slot, cut at a guessed boundary --------------------------------------
+    void reader_main() {
+        try {
+            Reader in(path_);
+            std::vector<uint8_t> carry;  // bytes behind the previous batch's cut
+            uint64_t seq = 0;
+            uint32_t fmt = 0;
+            bool eof = false;
+            while (!eof && !stop_.load()) {
+                {   // slot of batch `seq` is free once batch seq - G*S has been written
+                    std::unique_lock<std::mutex> l(slot_m_);
+                    slot_cv_.wait(l, [&] { return stop_.load() || written_ + (uint64_t)G_ * S_ > seq; });
+                    if (stop_.load()) break;
+                }
+                const auto t0 = Clock::now();
+                Batch b;
+                b.seq = seq;
+                b.gpu = (int)(seq % G_);
+                b.slot = (uint32_t)((seq / G_) % S_);
+                uint8_t* buf = gpus_[b.gpu].slot_host[b.slot];
+                if (carry.size() > reserve_) throw std::runtime_error("a single record is larger than the batch reserve");
+                b.off = reserve_ - carry.size();
+                std::memcpy(buf + b.off, carry.data(), carry.size());
+                uint64_t fill = reserve_;
+                while (fill < cap_) {
+                    size_t got = in.read(buf + fill, cap_ - fill);
+                    if (got == 0) { eof = true; break; }
+                    fill += got;
+                }
+                if (!eof) {  // learn about the end of the stream before deciding whether this batch is final
+                    uint8_t probe;
+                    if (in.read(&probe, 1) == 0) eof = true;
+                    else { peeked_ = true; peek_byte_ = probe; }
+                }
+                uint64_t n = fill - b.off;
+                if (seq == 0) {
+                    if (n == 0) { bad_flags_ = SBR_ST_INVALID_START; bad_record_ = 0; break; }  // empty input: needletail refuses it
+                    fmt = buf[b.off] == '>' ? SBR_FMT_FASTA : SBR_FMT_FASTQ;
+                }
+                carry.clear();
+                if (!eof) {
+                    uint64_t cut = guess_cut(buf + b.off, n, fmt, std::min<uint64_t>(reserve_, 1ull << 20));
+                    if (cut == 0) cut = n;  // no boundary in sight: let the scan decide
+                    carry.assign(buf + b.off + cut, buf + b.off + n);
+                    if (peeked_) { carry.push_back(peek_byte_); peeked_ = false; }
+                    n = cut;
+                }
+                b.n = n;
+                b.final_batch = eof;
+                if (stats_) { stats_->read_s += secs(t0, Clock::now()); stats_->bytes_in += n; }
+                if (n == 0 && eof && seq > 0) break;
+                filled_.push(b);
+                ++seq;
+            }
+        } catch (...) {
+            fail(std::current_exception());
+        }
+        filled_.close();
+    }
+
+    // ---- GPU thread: submit round-robin, wait in order, verify the guessed cuts ----------------------------------
+    void submit(Batch& b) {
+        Gpu& g = gpus_[b.gpu];
+        uint8_t* buf = g.slot_host[b.slot];
+        if (!prefix_.empty()) {  // the unconsumed tail of the previous batch goes in front
+            if (prefix_.size() > b.off) throw std::runtime_error("unconsumed tail does not fit in front of the next batch");
+            b.off -= prefix_.size();
+            b.n += prefix_.size();
+            std::memcpy(buf + b.off, prefix_.data(), prefix_.size());
+            prefix_.clear();
+        }
+        if (sbr_submit(g.ctx, b.slot, b.off, b.n, b.seq, b.final_batch ? 1 : 0) != SBR_OK)
+            throw std::runtime_error(std::string("sbr_submit failed: ") + sbr_last_error(g.ctx));
+    }
+    void wait(Batch& b) {
+        const auto t0 = Clock::now();
+        Gpu& g = gpus_[b.gpu];
+        if (sbr_wait(g.ctx, b.slot, &b.res) != SBR_OK)
+            throw std::runtime_error(std::string("sbr_wait failed: ") + sbr_last_error(g.ctx));
+        if (stats_) stats_->gpu_wait_s += secs(t0, Clock::now());
+    }
+    void gpu_main() {
+        std::deque<Batch> flight;
+        bool input_done = false;
+        while (!stop_.load()) {
+            Batch nb;
+            // keep every slot busy: take whatever the reader has ready
+            while (!input_done && flight.size() < (size_t)G_ * S_ && filled_.try_pop(nb)) {
+                submit(nb);
+                flight.push_back(nb);
+            }
+            if (flight.empty()) {
+                if (!filled_.pop(nb)) break;  // closed and drained
+                submit(nb);
+                flight.push_back(nb);
+                continue;
+            }
+            Batch b = flight.front();
+            flight.pop_front();
+            wait(b);
+            const bool errored = (b.res.status_flags & SBR_ST_ERROR_MASK) != 0;
+            if (!errored && b.res.consumed < b.n) {
+                // the guess was wrong (or the record capacity was hit): the rest belongs in front of the next batch
+                if (b.final_batch && !(b.res.status_flags & SBR_ST_REC_OVERFLOW))
+                    throw std::runtime_error("internal: final batch left bytes unconsumed without an error");
+                const uint8_t* buf = gpus_[b.gpu].slot_host[b.slot];
+                prefix_.assign(buf + b.off + b.res.consumed, buf + b.off + b.n);
+                if (b.res.consumed == 0) throw std::runtime_error("no progress: a single record is larger than a batch");
+                if (stats_) ++stats_->respeculated;
+                if (!flight.empty()) {  // the next batch already ran from a wrong start: run it again
+                    Batch& nx = flight.front();
+                    sbr_result dump;
+                    if (sbr_wait(gpus_[nx.gpu].ctx, nx.slot, &dump) != SBR_OK)
+                        throw std::runtime_error(std::string("sbr_wait failed: ") + sbr_last_error(gpus_[nx.gpu].ctx));
+                    submit(nx);
+                } else if (b.final_batch) {  // capacity overflow on the last batch: feed the rest as one more batch
+                    Batch extra = b;
+                    extra.seq = b.seq + 1;  // reuses the same slot after the writer is done with it: serialise
+                    pending_extra_ = true;
+                    extra_ = extra;
+                }
+            }
+            if (stats_) { ++stats_->batches; stats_->records += b.res.n_records; }
+            to_write_.push(b);
+            if (errored) { stop_after_error(); break; }
+            if (pending_extra_) run_extra();
+        }
+        // drain: results of batches behind an error are not wanted, but their slots must be quiet before teardown
+        for (auto& b : flight) {
+            sbr_result dump;
+            sbr_wait(gpus_[b.gpu].ctx, b.slot, &dump);
+        }
+    }
+    void stop_after_error() {
+        stop_.store(true);
+        slot_cv_.notify_all();
+    }
+    void run_extra() {  // rare: the last batch hit the record capacity; its rest is processed after the writer released the slot
+        pending_extra_ = false;
+        while (!prefix_.empty()) {
+            Batch b = extra_;
+            {
+                std::unique_lock<std::mutex> l(slot_m_);
+                slot_cv_.wait(l, [&] { return stop_.load() || written_ >= b.seq; });
+                if (stop_.load()) return;
+            }
+            uint8_t* buf = gpus_[b.gpu].slot_host[b.slot];
+            if (prefix_.size() > cap_ - reserve_) throw std::runtime_error("records too small for the configured record capacity");
+            b.off = reserve_;
+            b.n = prefix_.size();
+            std::memcpy(buf + b.off, prefix_.data(), prefix_.size());
+            prefix_.clear();
+            b.final_batch = true;
+            submit(b);
+            wait(b);
+            if (!(b.res.status_flags & SBR_ST_ERROR_MASK) && b.res.consumed < b.n) {
+                prefix_.assign(buf + b.off + b.res.consumed, buf + b.off + b.n);
+                extra_.seq = b.seq + 1;
+            }
+            if (stats_) { ++stats_->batches; stats_->records += b.res.n_records; }
+            to_write_.push(b);
+            if (b.res.status_flags & SBR_ST_ERROR_MASK) { stop_after_error(); return; }
+        }
+    }
+
+    // ---- writer: batches in order, bins in parallel ---------------------------------------------------------------
+    void write_bin(const Batch& b, uint32_t bin, uint32_t nok) {
+        const sbr_result& r = b.res;
+        const uint32_t lo = r.bin_start[bin], hi = r.bin_start[bin + 1];
+        if (lo == hi) return;
+        Sink& s = sinks_[bin];
+        const uint8_t* text = gpus_[b.gpu].slot_host[b.slot] + b.off;
+        s.raw.clear();
+        uint64_t nrec = 0;
+        const bool check = r.rec_key != nullptr;  // some record of the batch needs re-serialisation
+        for (uint32_t j = lo; j < hi; ++j) {
+            const uint32_t i = r.order[j];
+            if (i >= nok) continue;  // at or behind the first bad record: the reference never got there
+            const uint8_t* rec = text + r.rec_off[i];
+            const size_t len = r.rec_off[i + 1] - r.rec_off[i];
+            if (check && (r.fmt == SBR_FMT_FASTA || (r.rec_key[i] & (1ull << 49)))) canonical_record(rec, len, r.fmt, s.raw);
+            else s.raw.insert(s.raw.end(), rec, rec + len);
+            ++nrec;
+        }
+        if (!nrec) return;
+        const std::vector<uint8_t>* out = &s.raw;
+        if (out_format_ != Format::No) {
+            compress_member(out_format_, level_, s.raw.data(), s.raw.size(), s.packed);
+            out = &s.packed;
+        }
+        if (fwrite(out->data(), 1, out->size(), s.fh) != out->size()) throw std::runtime_error("write failed");
+        s.written_records += nrec;
+    }
+    void writer_main() {
+        try {
+            int nthreads = opt_.writer_threads > 0 ? opt_.writer_threads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+            Batch b;
+            while (to_write_.pop(b)) {
+                const auto t0 = Clock::now();
+                const sbr_result& r = b.res;
+                uint32_t nok = r.n_records;
+                if (r.status_flags & SBR_ST_ERROR_MASK) {
+                    nok = std::min(nok, r.first_bad_record);
+                    bad_flags_ = r.first_bad_flags;
+                    bad_record_ = records_before_ + r.first_bad_record;
+                }
+                std::atomic<uint32_t> next{0};
+                std::exception_ptr werr;
+                std::mutex wm;
+                auto work = [&] {
+                    try {
+                        for (uint32_t bin; (bin = next.fetch_add(1)) < n_bins_;) write_bin(b, bin, nok);
+                    } catch (...) {
+                        std::lock_guard<std::mutex> l(wm);
+                        werr = std::current_exception();
+                    }
+                };
+                const int nt = (int)std::min<uint32_t>((uint32_t)nthreads, n_bins_);
+                std::vector<std::thread> pool;
+                for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+                work();
+                for (auto& t : pool) t.join();
+                if (werr) std::rethrow_exception(werr);
+                records_before_ += r.n_records;
+                if (stats_) stats_->write_s += secs(t0, Clock::now());
+                {
+                    std::lock_guard<std::mutex> l(slot_m_);
+                    written_ = b.seq + 1;
+                }
+                slot_cv_.notify_all();
+            }
+            for (auto& s : sinks_) fflush(s.fh);
+        } catch (...) {
+            fail(std::current_exception());
+        }
+    }
+
+    std::string path_;
+    HostOptions opt_;
+    Format out_format_;
+    int level_;
+    RunStats* stats_;
+    uint32_t n_bins_ = 0;
+    int G_ = 1;
+    uint32_t S_ = 2;
+    uint64_t cap_ = 0, reserve_ = 0;
+    std::vector<Gpu> gpus_;
+    std::vector<Sink> sinks_;
+    Channel<Batch> filled_, to_write_;
+    std::mutex slot_m_;
+    std::condition_variable slot_cv_;
+    uint64_t written_ = 0;  // batches fully written (== next sequence number the writer expects)
+    std::atomic<bool> stop_{false};
+    std::mutex err_m_;
+    std::exception_ptr error_;
+    std::vector<uint8_t> prefix_;
+    bool peeked_ = false;
+    uint8_t peek_byte_ = 0;
+    bool pending_extra_ = false;
+    Batch extra_;
+    uint32_t bad_flags_ = 0;
+    uint64_t bad_record_ = 0, records_before_ = 0;
+};
+
+std::vector<std::string> barcode_list(const Barcode& bd) {
+    if (bd.rows.empty()) throw std::runtime_error("Barcode data is empty");  // demux.rs:31-33
+    std::vector<std::string> v;
+    for (auto& r : bd.rows) v.push_back(r.barcode);
+    return v;
+}
+
+}  // namespace
+
+std::pair<Counts&, bool> se_demux(const std::string& file, Format format, int level, Barcode& bd, uint8_t mismatch,
+                                  Counts& nb_records, const HostOptions& opt, RunStats* stats) {
+    const Format original = which_format(file);
+    if (format == Format::No) format = original;  // demux.rs:26-29
+    const auto bcs = barcode_list(bd);
+    if (bd.unknown.empty()) throw std::runtime_error("Missing 'XXX' fallback barcode entry in barcode_data");  // demux.rs:43-46
+    std::vector<FILE*> files;
+    for (auto& r : bd.rows) files.push_back(r.files.at(0).fh);
+    files.push_back(bd.unknown.at(0).fh);
+    Pass pass(file, files, bcs, mismatch, format, level, opt, stats);
+    const bool unk_empty = pass.run(/*strict=*/true, nb_records, bcs);
+    return {nb_records, unk_empty};
+}
+
+std::pair<Counts&, std::string> pe_demux(const std::string& forward, const std::string& reverse, Format format, int level,
+                                         Barcode& bd, uint8_t mismatch, Counts& nb_records, const HostOptions& opt,
+                                         RunStats* stats) {
+    Format compression = which_format(forward);  // both mates are written with the forward-derived format (demux.rs:81,95-97)
+    (void)which_format(reverse);
+    if (format != Format::No) compression = format;
+    const auto bcs = barcode_list(bd);
+    if (bd.unknown.size() < 2) throw std::runtime_error("Missing 'XXX' fallback barcode entry in barcode_data");
+    bool unk[2];
+    for (int mate = 0; mate < 2; ++mate) {  // forward pass, then reverse pass (demux.rs:101-110, 114-123)
+        std::vector<FILE*> files;
+        for (auto& r : bd.rows) files.push_back(r.files.at(mate).fh);
+        files.push_back(bd.unknown.at(mate).fh);
+        Pass pass(mate == 0 ? forward : reverse, files, bcs, mismatch, compression, level, opt, stats);
+        unk[mate] = pass.run(/*strict=*/false, nb_records, bcs);
+    }
+    return {nb_records, std::string(unk[0] ? "true" : "false") + (unk[1] ? "true" : "false")};
+}
+
+}  // namespace sabreur

@@ -1,0 +1,207 @@
+"""GPU tests of the `sabreur` command line (C++ host over the C ABI): output files against the reference's derived
+goldens and against the oracle's per-barcode output bytes, single- and paired-end, every output
+format (compared after decompression, hazard H9), multi-batch runs with guessed cuts, error semantics."""
+import bz2
+import gzip
+import hashlib
+import lzma
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import FIXTURES, ROOT, fixture_bytes, read_barcode_table
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+SABREUR = os.path.join(ROOT, "sabreur_b200", "bin", "sabreur")
+SELFTEST = os.path.join(ROOT, "sabreur_b200", "bin", "codec_selftest")
+
+R1_GOLD = [(82312, "90d9764b8b69432c"), (83351, "dd06fd51837741d1"), (83359, "98a7be33c3ac7170"),
+           (83325, "5af261ae384d0e8d"), (83320, "cf6171f02f1974ce"), (83354, "8a8208327d1ba4cc"),
+           (83302, "d88301f0531c93a4"), (83347, "9e490c81cc82b11e"), (83316, "88d17addc88d6666"),
+           (83327, "5a32eafb431d020f")]
+R2_GOLD = ["3686079bca97996c", "7fc5a66ffdfe6101", "8293662d5bd9b6b4", "98e65e4c22cb35df", "1cc04b3230073339",
+           "d4e226dd2f2c9917", "5e5fc12f2bbaebba", "4a4c0bd82078af82", "87f8a9ac4c20bd39", "c7969e3ae26f42ac"]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("gpu-marked test without a CUDA device")
+    if not os.path.exists(SABREUR):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "sabreur_b200", "csrc", "host")])
+
+
+def _fx(name):
+    return os.path.join(FIXTURES, name)
+
+
+def _run(args, cwd, ok=True):
+    r = subprocess.run([SABREUR] + [str(a) for a in args], capture_output=True, text=True, cwd=cwd)
+    if ok:
+        assert r.returncode == 0, r.stdout + r.stderr
+    return r
+
+
+def _plain(path):
+    data = open(path, "rb").read()
+    if path.endswith(".gz"):
+        return gzip.decompress(data) if data else b""
+    if path.endswith(".bz2"):
+        return bz2.decompress(data) if data else b""
+    if path.endswith(".xz"):
+        return lzma.decompress(data) if data else b""
+    if path.endswith(".zst"):
+        return subprocess.run([SELFTEST, "cat", path], capture_output=True, check=True).stdout if data else b""
+    return data
+
+
+def _sha(b):
+    return hashlib.sha256(b).hexdigest()[:16]
+
+
+def test_cfg1_test_fq_bc_se_m0(tmp_path):
+    """BASELINE configs[0]: ten empty barcode files, unknown.fa byte-identical to the input, no count lines"""
+    r = _run([_fx("bc_se.txt"), _fx("test.fq"), "-o", "out"], tmp_path)
+    rows = read_barcode_table("bc_se.txt")
+    for row in rows:
+        assert os.path.getsize(tmp_path / "out" / row[1]) == 0
+    assert open(tmp_path / "out" / "unknown.fa", "rb").read() == fixture_bytes("test.fq")
+    assert "records found for barcode" not in r.stdout
+    assert "starting up in single-end mode" in r.stdout and "Thanks. Share. Come again!" in r.stdout
+
+
+@pytest.mark.parametrize("name", ["reads_1.fa.gz", "reads_1.fa.bz2", "reads_1.fa.xz"])
+def test_reads_1_se_goldens_keep_input_compression(tmp_path, name):
+    """no -f: outputs take the input's compression (main.rs:28, demux.rs:26-29); content == SURVEY 8c goldens"""
+    ext = os.path.splitext(name)[1]
+    r = _run([_fx("bc_se.txt"), _fx(name), "-o", "out"], tmp_path)
+    rows = read_barcode_table("bc_se.txt")
+    got = []
+    for row in rows:
+        b = _plain(str(tmp_path / "out" / (row[1] + ext)))
+        got.append((len(b), _sha(b)))
+    assert got == R1_GOLD
+    assert not os.path.exists(tmp_path / "out" / ("unknown.fa" + ext))  # empty -> deleted (main.rs:179-181)
+    assert "1000 records found for barcode GTCTGATG" in r.stdout and r.stdout.count("999 records found") == 9
+
+
+@pytest.mark.parametrize("fmt", ["gz", "xz", "bz2", "zst"])
+def test_pe_fixture_every_output_format(tmp_path, fmt):
+    r = _run([_fx("bc_pe_fa.txt"), _fx("reads_1.fa.gz"), _fx("reads_2.fa.gz"), "-o", "out", "-f", fmt, "-l", "3"], tmp_path)
+    rows = read_barcode_table("bc_pe_fa.txt")
+    g1 = [_sha(_plain(str(tmp_path / "out" / f"{row[1]}.{fmt}"))) for row in rows]
+    g2 = [_sha(_plain(str(tmp_path / "out" / f"{row[2]}.{fmt}"))) for row in rows]
+    assert g1 == [s for _, s in R1_GOLD] and g2 == R2_GOLD
+    assert "starting up in paired-end mode" in r.stdout and f"Output files will .{fmt} compressed" in r.stdout
+    assert "2000 records found for barcode GTCTGATG" in r.stdout and r.stdout.count("1998 records found") == 9
+    assert not os.path.exists(tmp_path / "out" / f"unknown_R1.fa.{fmt}") and not os.path.exists(tmp_path / "out" / f"unknown_R2.fa.{fmt}")
+
+
+def _synthetic_file(tmp_path, w_name, n, mate=0, compress=None):
+    from sabreur_b200 import synth
+    w = synth.WORKLOADS[w_name]
+    tab = synth.table(w)
+    text = synth.reads_host(w, tab, 4242, n, mate).tobytes()
+    bcs = [bytes(r) for r in tab]
+    p = tmp_path / f"reads_{mate}.txt"
+    if compress == "gz":
+        p = tmp_path / f"reads_{mate}.txt.gz"
+        with gzip.open(p, "wb", compresslevel=1) as fh:
+            fh.write(text)
+    else:
+        p.write_bytes(text)
+    tsv = tmp_path / "bc.tsv"
+    tsv.write_text("".join(f"{b.decode()}\tb{i}_R1.fq\tb{i}_R2.fq\n" for i, b in enumerate(bcs)))
+    return w, bcs, text, str(p), str(tsv)
+
+
+@pytest.mark.parametrize("w_name,n,batch_mb", [("cfg3", 40000, 1), ("cfg5", 50000, 2), ("cfg3", 30000, 256)])
+def test_synthetic_se_multi_batch_equals_oracle(tmp_path, w_name, n, batch_mb):
+    """many batches with guessed cuts (two slots in flight): every output file == the oracle's bytes"""
+    w, bcs, text, path, tsv = _synthetic_file(tmp_path, w_name, n)
+    r = _run([tsv, path, "-o", "out", "-m", w.mismatch, "--batch-mb", batch_mb, "--timing"], tmp_path)
+    outs = orc.demux_outputs(text, bcs, w.mismatch)
+    for i, b in enumerate(bcs):
+        assert open(tmp_path / "out" / f"b{i}_R1.fq", "rb").read() == outs[i], f"bin {i}"
+    unk = tmp_path / "out" / "unknown.fa"
+    assert (open(unk, "rb").read() if os.path.exists(unk) else b"") == outs[-1]
+    assert f"Allowing up to {w.mismatch} mismatches" in r.stdout
+    assert "re-submitted" in r.stderr
+
+
+def test_synthetic_pe_gz_in_zst_out(tmp_path):
+    """BASELINE configs[1] substitute: synthetic PE FASTQ, gzip input, the in-tree 48 x 8 table, --mismatch 1"""
+    from sabreur_b200 import synth
+    w = synth.CFG4
+    rows = read_barcode_table("bc_pe_fq.txt")
+    bcs = [r[0].encode() for r in rows]
+    tab = np.frombuffer(b"".join(bcs), dtype=np.uint8).reshape(len(bcs), -1)
+    texts = [synth.reads_host(w, tab, 99, 20000, mate).tobytes() for mate in (0, 1)]
+    paths = []
+    for mate, t in enumerate(texts):
+        p = tmp_path / f"in_R{mate + 1}.fastq.gz"
+        with gzip.open(p, "wb", compresslevel=1) as fh:
+            fh.write(t)
+        paths.append(str(p))
+    _run([_fx("bc_pe_fq.txt"), paths[0], paths[1], "-o", "out", "-m", 1, "-f", "zst", "--batch-mb", 2], tmp_path)
+    for mate, t in enumerate(texts):
+        outs = orc.demux_outputs(t, bcs, 1)
+        for i, row in enumerate(rows):
+            assert _plain(str(tmp_path / "out" / (row[1 + mate] + ".zst"))) == outs[i]
+        unk = str(tmp_path / "out" / f"unknown_R{mate + 1}.fa.zst")
+        assert (_plain(unk) if os.path.exists(unk) else b"") == outs[-1]
+
+
+def test_noncanonical_input_is_reserialised(tmp_path):
+    """CRLF line ends, '+id' separator lines and a missing final newline: outputs are needletail's canonical bytes"""
+    recs = [(b"r%d extra" % i, b"ACGTACGTAC"[i % 3:] + b"GGTT" * (i % 5 + 1)) for i in range(300)]
+    text = b"".join(b"@" + h + b"\r\n" + s + b"\r\n+" + h + b"\r\n" + b"I" * len(s) + b"\r\n" for h, s in recs)[:-2]
+    p = tmp_path / "in.fq"
+    p.write_bytes(text)
+    tsv = tmp_path / "bc.tsv"
+    bcs = [b"ACGT", b"CGTA", b"GTAC"]
+    tsv.write_text("".join(f"{b.decode()}\to{i}.fq\n" for i, b in enumerate(bcs)))
+    _run([str(tsv), str(p), "-o", "out", "--batch-mb", 1], tmp_path)
+    outs = orc.demux_outputs(text, bcs, 0)
+    for i in range(3):
+        got = open(tmp_path / "out" / f"o{i}.fq", "rb").read()
+        assert got == outs[i] and b"\r" not in got
+    assert not os.path.exists(tmp_path / "out" / "unknown.fa") or open(tmp_path / "out" / "unknown.fa", "rb").read() == outs[-1]
+
+
+def test_se_parse_error_exits_1_after_writing_the_good_records(tmp_path):
+    good = b"@a\nACGTAA\n+\nIIIIII\n@b\nCCGTAA\n+\nIIIIII\n"
+    bad = good + b"@c\nACGTAA\n-\nIIIIII\n@d\nACGTAA\n+\nIIIIII\n"
+    p = tmp_path / "bad.fq"
+    p.write_bytes(bad)
+    tsv = tmp_path / "bc.tsv"
+    tsv.write_text("ACGT\tx.fq\n")
+    r = _run([str(tsv), str(p), "-o", "out"], tmp_path, ok=False)
+    assert r.returncode == 1 and "Error:" in r.stderr
+    assert open(tmp_path / "out" / "x.fq", "rb").read() == b"@a\nACGTAA\n+\nIIIIII\n"
+    assert open(tmp_path / "out" / "unknown.fa", "rb").read() == b"@b\nCCGTAA\n+\nIIIIII\n"
+
+
+def test_short_read_is_the_reference_panic(tmp_path):
+    p = tmp_path / "short.fq"
+    p.write_bytes(b"@a\nACGTAA\n+\nIIIIII\n@b\nAC\n+\nII\n")
+    tsv = tmp_path / "bc.tsv"
+    tsv.write_text("ACGT\tx.fq\n")
+    r = _run([str(tsv), str(p), "-o", "out"], tmp_path, ok=False)
+    assert r.returncode == 101 and "panicked" in r.stderr
+
+
+def test_duplicate_barcode_rows_keep_the_last_rows_file(tmp_path):
+    """H7: HashMap::insert replaces the files of a repeated key (main.rs:149); the first row's file stays empty"""
+    p = tmp_path / "in.fq"
+    p.write_bytes(b"@a\nACGTAA\n+\nIIIIII\n")
+    tsv = tmp_path / "bc.tsv"
+    tsv.write_text("ACGT\tfirst.fq\nACGT\tsecond.fq\n")
+    _run([str(tsv), str(p), "-o", "out"], tmp_path)
+    assert os.path.getsize(tmp_path / "out" / "first.fq") == 0
+    assert open(tmp_path / "out" / "second.fq", "rb").read() == b"@a\nACGTAA\n+\nIIIIII\n"

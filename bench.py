@@ -63,7 +63,7 @@ class Clocks:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -205,6 +205,10 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the demux path has no CPU fallback")
+    # stdout carries exactly ONE JSON line: whatever libraries print there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -276,7 +280,6 @@ def main():
     torch.cuda.synchronize()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    clk = clocks.stop()
     kms, nb_timed, launches = dm.timing()
     value = world * units * args.steps / (ms * 1e-3)
 
@@ -361,6 +364,8 @@ def main():
                "how": "pinned host text -> sbr_submit (H2D, scan, match, partition) -> sbr_wait (D2H rec_off, assign, order)"}
         dm2.close()
 
+    clk = clocks.stop()  # sampled over both timed regions (HBM-resident steps and the end-to-end steps)
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -389,7 +394,10 @@ def main():
                        "match": "xor+popc table walk" if args.no_lut else "first-match LUT built by the xor+popc kernel"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": int(launches),
         }
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     dm.close()
     if world > 1:
         dist.destroy_process_group()

@@ -41,7 +41,8 @@ def _fx(name):
 
 
 def _run(args, cwd, ok=True):
-    r = subprocess.run([SABREUR] + [str(a) for a in args], capture_output=True, text=True, cwd=cwd)
+    extra = os.environ.get("SABREUR_EXTRA_ARGS", "").split()  # e.g. "--gpus 2" on a multi-GPU box
+    r = subprocess.run([SABREUR] + [str(a) for a in args] + extra, capture_output=True, text=True, cwd=cwd)
     if ok:
         assert r.returncode == 0, r.stdout + r.stderr
     return r

@@ -62,7 +62,8 @@ struct Batch {
     int gpu = 0;
     uint32_t slot = 0;
     uint64_t off = 0, n = 0;  // the batch is slot_host[off .. off + n)
-    bool final_batch = false;
+    bool final_batch = false;   // the stream ends with this batch
+    bool exact_end = false;     // the batch ends exactly at a record boundary (FASTA cut in front of a '>' line)
     sbr_result res{};
 };
 
@@ -157,8 +158,8 @@ void canonical_record(const uint8_t* r, size_t n, uint32_t fmt, std::vector<uint
 
 struct Sink {  // where the records of one bin go in this pass
     FILE* fh = nullptr;
-    std::vector<uint8_t> raw, packed;
-    uint64_t written_records = 0;
+    std::vector<uint8_t> raw;
+    uint64_t written_records = 0, batch_records = 0;
 };
 
 class Pass {
@@ -297,6 +298,10 @@ private:
                     if (cut == 0) cut = n;  // no boundary in sight: let the scan decide
                     carry.assign(buf + b.off + cut, buf + b.off + n);
                     if (peeked_) { carry.push_back(peek_byte_); peeked_ = false; }
+                    // FASTA: a line that starts with '>' IS a record start (no guess involved), so the batch in front
+                    // of it is submitted as "ends at a record boundary"; a non-final FASTA batch would otherwise hold
+                    // its last record back as possibly incomplete
+                    b.exact_end = fmt == SBR_FMT_FASTA && cut < n;
                     n = cut;
                 }
                 b.n = n;
@@ -323,7 +328,7 @@ private:
             std::memcpy(buf + b.off, prefix_.data(), prefix_.size());
             prefix_.clear();
         }
-        if (sbr_submit(g.ctx, b.slot, b.off, b.n, b.seq, b.final_batch ? 1 : 0) != SBR_OK)
+        if (sbr_submit(g.ctx, b.slot, b.off, b.n, b.seq, (b.final_batch || b.exact_end) ? 1 : 0) != SBR_OK)
             throw std::runtime_error(std::string("sbr_submit failed: ") + sbr_last_error(g.ctx));
     }
     void wait(Batch& b) {
@@ -417,16 +422,17 @@ private:
         }
     }
 
-    // ---- writer: batches in order, bins in parallel ---------------------------------------------------------------
-    void write_bin(const Batch& b, uint32_t bin, uint32_t nok) {
+    // ---- writer: batches in order; gather per bin and compress per 4 MB member in parallel, append in order --------
+    void gather_bin(const Batch& b, uint32_t bin, uint32_t nok) {
         const sbr_result& r = b.res;
+        Sink& s = sinks_[bin];
+        s.raw.clear();
+        s.batch_records = 0;
         const uint32_t lo = r.bin_start[bin], hi = r.bin_start[bin + 1];
         if (lo == hi) return;
-        Sink& s = sinks_[bin];
         const uint8_t* text = gpus_[b.gpu].slot_host[b.slot] + b.off;
-        s.raw.clear();
-        uint64_t nrec = 0;
         const bool check = r.rec_key != nullptr;  // some record of the batch needs re-serialisation
+        s.raw.reserve((size_t)(r.rec_off[r.order[hi - 1] + 1] - r.rec_off[r.order[lo]]) / 4 + 4096);
         for (uint32_t j = lo; j < hi; ++j) {
             const uint32_t i = r.order[j];
             if (i >= nok) continue;  // at or behind the first bad record: the reference never got there
@@ -434,20 +440,34 @@ private:
             const size_t len = r.rec_off[i + 1] - r.rec_off[i];
             if (check && (r.fmt == SBR_FMT_FASTA || (r.rec_key[i] & (1ull << 49)))) canonical_record(rec, len, r.fmt, s.raw);
             else s.raw.insert(s.raw.end(), rec, rec + len);
-            ++nrec;
+            ++s.batch_records;
         }
-        if (!nrec) return;
-        const std::vector<uint8_t>* out = &s.raw;
-        if (out_format_ != Format::No) {
-            compress_member(out_format_, level_, s.raw.data(), s.raw.size(), s.packed);
-            out = &s.packed;
-        }
-        if (fwrite(out->data(), 1, out->size(), s.fh) != out->size()) throw std::runtime_error("write failed");
-        s.written_records += nrec;
+    }
+    template <class F>
+    void parallel_for(uint32_t n, int nthreads, F&& body) {
+        std::atomic<uint32_t> next{0};
+        std::exception_ptr werr;
+        std::mutex wm;
+        auto work = [&] {
+            try {
+                for (uint32_t i; (i = next.fetch_add(1)) < n;) body(i);
+            } catch (...) {
+                std::lock_guard<std::mutex> l(wm);
+                werr = std::current_exception();
+            }
+        };
+        const int nt = (int)std::min<uint32_t>((uint32_t)nthreads, n);
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+        work();
+        for (auto& t : pool) t.join();
+        if (werr) std::rethrow_exception(werr);
     }
     void writer_main() {
         try {
-            int nthreads = opt_.writer_threads > 0 ? opt_.writer_threads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+            const int nthreads = opt_.writer_threads > 0 ? opt_.writer_threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+            constexpr size_t MEMBER = 4u << 20;  // raw bytes per compressed member
+            struct Piece { uint32_t bin; size_t lo, hi; std::vector<uint8_t> packed; };
             Batch b;
             while (to_write_.pop(b)) {
                 const auto t0 = Clock::now();
@@ -458,23 +478,24 @@ private:
                     bad_flags_ = r.first_bad_flags;
                     bad_record_ = records_before_ + r.first_bad_record;
                 }
-                std::atomic<uint32_t> next{0};
-                std::exception_ptr werr;
-                std::mutex wm;
-                auto work = [&] {
-                    try {
-                        for (uint32_t bin; (bin = next.fetch_add(1)) < n_bins_;) write_bin(b, bin, nok);
-                    } catch (...) {
-                        std::lock_guard<std::mutex> l(wm);
-                        werr = std::current_exception();
-                    }
-                };
-                const int nt = (int)std::min<uint32_t>((uint32_t)nthreads, n_bins_);
-                std::vector<std::thread> pool;
-                for (int t = 1; t < nt; ++t) pool.emplace_back(work);
-                work();
-                for (auto& t : pool) t.join();
-                if (werr) std::rethrow_exception(werr);
+                parallel_for(n_bins_, nthreads, [&](uint32_t bin) { gather_bin(b, bin, nok); });
+                if (out_format_ == Format::No) {
+                    for (auto& s : sinks_)
+                        if (!s.raw.empty() && fwrite(s.raw.data(), 1, s.raw.size(), s.fh) != s.raw.size()) throw std::runtime_error("write failed");
+                } else {
+                    std::vector<Piece> pieces;  // in (bin, offset) order: members of a file are appended in this order
+                    for (uint32_t bin = 0; bin < n_bins_; ++bin)
+                        for (size_t lo = 0; lo < sinks_[bin].raw.size(); lo += MEMBER)
+                            pieces.push_back(Piece{bin, lo, std::min(lo + MEMBER, sinks_[bin].raw.size()), {}});
+                    parallel_for((uint32_t)pieces.size(), nthreads, [&](uint32_t k) {
+                        Piece& pc = pieces[k];
+                        compress_member(out_format_, level_, sinks_[pc.bin].raw.data() + pc.lo, pc.hi - pc.lo, pc.packed);
+                    });
+                    for (auto& pc : pieces)
+                        if (fwrite(pc.packed.data(), 1, pc.packed.size(), sinks_[pc.bin].fh) != pc.packed.size())
+                            throw std::runtime_error("write failed");
+                }
+                for (auto& s : sinks_) s.written_records += s.batch_records;
                 records_before_ += r.n_records;
                 if (stats_) stats_->write_s += secs(t0, Clock::now());
                 {

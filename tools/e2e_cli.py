@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""End-to-end wall time of the `sabreur` command line on a synthetic file, I/O share visible.
+
+  python tools/e2e_cli.py [--workload cfg3] [--reads 4000000] [--in-format gz|plain] [--out-format zst|gz|none] [--gpus 1]
+
+Writes the input with the library's own generator, runs the CLI with --timing and prints one JSON line:
+wall seconds, reads/s, and the host's split (read+decompress / waiting for the GPU / gather+compress+write).
+The GPU kernels are a rounding error here: decompression and compression on the host cores are the wall."""
+import argparse
+import gzip
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="cfg3")
+    ap.add_argument("--reads", type=int, default=4_000_000)
+    ap.add_argument("--in-format", default="gz", choices=["gz", "plain"])
+    ap.add_argument("--out-format", default="none", choices=["none", "gz", "zst", "bz2", "xz"])
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--batch-mb", type=int, default=256)
+    a = ap.parse_args()
+    from sabreur_b200 import synth
+    w = synth.WORKLOADS[a.workload]
+    tab = synth.table(w)
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+        paths = []
+        for mate in ((0, 1) if w.paired else (0,)):
+            p = os.path.join(d, f"in_R{mate + 1}." + ("fa" if w.fmt == 1 else "fq") + (".gz" if a.in_format == "gz" else ""))
+            opener = (lambda q: gzip.open(q, "wb", compresslevel=1)) if a.in_format == "gz" else (lambda q: open(q, "wb"))
+            with opener(p) as fh:
+                for lo in range(0, a.reads, 500_000):
+                    fh.write(synth.reads_host(w, tab, lo, min(500_000, a.reads - lo), mate).tobytes())
+            paths.append(p)
+        tsv = os.path.join(d, "bc.tsv")
+        with open(tsv, "w") as fh:
+            for i, row in enumerate(tab):
+                fh.write(f"{bytes(row).decode()}\tbc{i}_R1\tbc{i}_R2\n")
+        cmd = [os.path.join(ROOT, "sabreur_b200", "bin", "sabreur"), tsv] + paths + \
+              ["-o", os.path.join(d, "out"), "-m", str(w.mismatch), "--gpus", str(a.gpus), "--batch-mb", str(a.batch_mb), "--timing", "-q"]
+        if a.out_format != "none":
+            cmd += ["-f", a.out_format]
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd, capture_output=True, text=True, cwd=d)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            sys.exit(r.stdout + r.stderr)
+        m = re.search(r"timing: total ([\d.]+) s \| read\+decompress ([\d.]+) s \| waiting for the GPU ([\d.]+) s \| gather\+compress\+write ([\d.]+) s \| (\d+) bytes in, (\d+) records, (\d+) batches, (\d+) re-submitted", r.stderr)
+        total, rd, gw, wr, nbytes, nrec, nb, resub = (float(x) for x in m.groups())
+        in_bytes = sum(os.path.getsize(p) for p in paths)
+        out_bytes = sum(os.path.getsize(os.path.join(d, "out", f)) for f in os.listdir(os.path.join(d, "out")))
+        print(json.dumps({
+            "what": "sabreur CLI end to end (host decompression -> GPU demux -> host compression -> files)",
+            "workload": w.name, "reads": int(nrec), "in_format": a.in_format, "out_format": a.out_format, "gpus": a.gpus,
+            "wall_s": wall, "reads_per_s": nrec / wall, "input_file_bytes": in_bytes, "text_bytes": int(nbytes), "output_bytes": out_bytes,
+            "host_threads": os.cpu_count(),
+            "pipeline_s": {"total": total, "reader_decompress": rd, "gpu_thread_waiting": gw, "writer_gather_compress_write": wr},
+            "batches": int(nb), "resubmitted": int(resub),
+            "note": "reader, GPU thread and writer run concurrently: the stages overlap, the slowest one is the wall"}))
+
+
+if __name__ == "__main__":
+    main()

@@ -24,7 +24,8 @@ uint32_t scan_fast_regions(uint32_t nbytes, int max_regions, uint32_t* tiles_per
 cudaError_t scan_fast_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbytes, uint32_t max_records, uint32_t cap_r,
                              uint32_t n_regions, uint32_t tiles_per_region, uint32_t extra_regions, uint32_t bc_len,
                              uint32_t packed, uint32_t final_batch, BatchHeader* hdr, RegionInfo* info, uint32_t* region_base,
-                             uint32_t* seg_rec_off, uint64_t* seg_key, uint32_t* rec_off_dense, cudaStream_t stream);
+                             uint32_t* seg_rec_off, uint64_t* seg_key, uint32_t* rec_off_dense, uint4* lookback_desc,
+                             uint32_t n_desc, cudaStream_t stream);
 // k_match.cu
 struct MatchLaunch {
     const uint64_t* key_dense; const uint64_t* seg_key; const uint32_t* seg_rec_off; const uint32_t* region_base;
@@ -33,7 +34,7 @@ struct MatchLaunch {
     const uint2* tab; const uint16_t* lut; const uint8_t* rows; const uint32_t* lens;
     uint32_t n, m, k, stride;
     const uint8_t* text; uint32_t nbytes;
-    uint16_t* assign; uint32_t* rec_off; uint64_t* key_out; uint32_t* cnt; uint32_t nbins;
+    uint16_t* assign; uint32_t* rec_off; uint64_t* key_out; uint32_t* cnt; uint32_t* cta_cnt; uint32_t nbins;
     int grid;
 };
 size_t match_smem(uint32_t n, uint32_t stride, uint32_t nbins, bool generic);
@@ -45,12 +46,13 @@ struct PartitionPlan {
     int grid;
     uint32_t V;
     size_t smem;
+    uint32_t nbits;
 };
 PartitionPlan partition_plan(uint32_t nbins, uint32_t max_records, int sms);
 cudaError_t partition_prepare();
 cudaError_t partition_launch(const uint16_t* d_assign, const BatchHeader* d_hdr, uint32_t nbins, uint32_t* d_cnt,
-                             uint32_t* d_bin_count, uint32_t* d_bin_start, uint32_t* d_order, uint32_t* d_done_counter,
-                             const PartitionPlan& p, cudaStream_t stream);
+                             uint32_t* d_cta_cnt, uint32_t* d_bin_count, uint32_t* d_bin_start, uint32_t* d_order,
+                             uint32_t* d_done_counter, const PartitionPlan& p, cudaStream_t stream);
 }  // namespace sbr
 
 using namespace sbr;
@@ -72,6 +74,7 @@ struct Slot {
     uint64_t* d_key = nullptr;
     uint16_t* d_assign = nullptr;
     uint32_t* d_cnt = nullptr;
+    uint32_t* d_cta_cnt = nullptr;
     uint32_t* d_bin_count = nullptr;
     uint32_t* d_bin_start = nullptr;
     uint32_t* d_order = nullptr;
@@ -170,7 +173,7 @@ static void free_slot(Slot& s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFree(s.d_text); cudaFree(s.d_hdr); cudaFree(s.d_desc); cudaFree(s.d_rec_off); cudaFree(s.d_key);
     cudaFree(s.d_done); cudaFree(s.d_info); cudaFree(s.d_region_base); cudaFree(s.d_seg_rec_off); cudaFree(s.d_seg_key);
-    cudaFree(s.d_assign); cudaFree(s.d_cnt); cudaFree(s.d_bin_count); cudaFree(s.d_bin_start); cudaFree(s.d_order);
+    cudaFree(s.d_assign); cudaFree(s.d_cnt); cudaFree(s.d_cta_cnt); cudaFree(s.d_bin_count); cudaFree(s.d_bin_start); cudaFree(s.d_order);
     cudaFreeHost(s.h_text); cudaFreeHost(s.h_hdr); cudaFreeHost(s.h_rec_off); cudaFreeHost(s.h_key);
     cudaFreeHost(s.h_assign); cudaFreeHost(s.h_bin_count); cudaFreeHost(s.h_bin_start); cudaFreeHost(s.h_order);
     if (s.hdr_ready) cudaEventDestroy(s.hdr_ready);
@@ -274,6 +277,7 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
         CU(c, cudaMalloc(&s.d_key, (mr + 4) * sizeof(uint64_t)));
         CU(c, cudaMalloc(&s.d_assign, (mr + 4) * sizeof(uint16_t)));
         CU(c, cudaMalloc(&s.d_cnt, (size_t)c->nbins * c->plan.V * sizeof(uint32_t)));
+        CU(c, cudaMalloc(&s.d_cta_cnt, (size_t)c->nbins * c->plan.grid * sizeof(uint32_t)));
         CU(c, cudaMalloc(&s.d_bin_count, c->nbins * sizeof(uint32_t)));
         CU(c, cudaMalloc(&s.d_bin_start, (c->nbins + 1) * sizeof(uint32_t)));
         CU(c, cudaMalloc(&s.d_order, (mr + 1) * sizeof(uint32_t)));
@@ -343,7 +347,9 @@ static int launch_pipeline(sbr_ctx* c, Slot& s, const uint8_t* d_text, uint32_t 
     cudaEvent_t* ev = nullptr;
     if (c->timing && c->ev_used < TIMING_RING) ev = &c->ev[(size_t)c->ev_used++ * 4];
     CU(c, cudaMemsetAsync(s.d_hdr, 0, sizeof(BatchHeader), st));
-    CU(c, cudaMemsetAsync(s.d_desc, 0, (size_t)scan_tiles(nbytes) * sizeof(uint4), st));
+    // the look-back scan's tile descriptors: zeroed here only when that scan is forced; otherwise k_scan_finish clears
+    // them in the rare case it hands the batch over
+    if (c->exact_only) CU(c, cudaMemsetAsync(s.d_desc, 0, (size_t)scan_tiles(nbytes) * sizeof(uint4), st));
     if (ev) CU(c, cudaEventRecord(ev[0], st));
     uint32_t cap_r = 0;
     if (!c->exact_only) {
@@ -353,7 +359,7 @@ static int launch_pipeline(sbr_ctx* c, Slot& s, const uint8_t* d_text, uint32_t 
         cap_r = (uint32_t)(((uint64_t)c->max_records * 5 / 4) / nreg) + 64;
         CU(c, scan_fast_launch(fmt, d_text, nbytes, c->max_records, cap_r, nreg, tpr, extra, c->cfg.bc_len, c->packed ? 1u : 0u,
                                (uint32_t)final_batch, s.d_hdr, s.d_info, s.d_region_base, s.d_seg_rec_off, s.d_seg_key,
-                               s.d_rec_off, st));
+                               s.d_rec_off, s.d_desc, scan_tiles(nbytes), st));
         c->launches += 2;
     }
     // the look-back scan: unconditional when forced, otherwise it returns at once unless the fast scan gave up
@@ -368,13 +374,13 @@ static int launch_pipeline(sbr_ctx* c, Slot& s, const uint8_t* d_text, uint32_t 
         L.tab = c->packed ? c->d_tab : nullptr; L.lut = c->d_lut; L.rows = c->d_rows; L.lens = c->d_lens;
         L.n = c->cfg.n_barcodes; L.m = c->cfg.mismatch; L.k = c->cfg.bc_len; L.stride = c->cfg.bc_len;
         L.text = d_text; L.nbytes = nbytes;
-        L.assign = s.d_assign; L.rec_off = s.d_rec_off; L.key_out = s.d_key; L.cnt = s.d_cnt; L.nbins = c->nbins;
+        L.assign = s.d_assign; L.rec_off = s.d_rec_off; L.key_out = s.d_key; L.cnt = s.d_cnt; L.cta_cnt = s.d_cta_cnt; L.nbins = c->nbins;
         L.grid = c->plan.grid;
         CU(c, match_launch(L, st));
     }
     if (ev) CU(c, cudaEventRecord(ev[2], st));
-    CU(c, partition_launch(s.d_assign, s.d_hdr, c->nbins, s.d_cnt, s.d_bin_count, s.d_bin_start, s.d_order, s.d_done,
-                           c->plan, st));
+    CU(c, partition_launch(s.d_assign, s.d_hdr, c->nbins, s.d_cnt, s.d_cta_cnt, s.d_bin_count, s.d_bin_start, s.d_order,
+                           s.d_done, c->plan, st));
     if (ev) CU(c, cudaEventRecord(ev[3], st));
     c->launches += (fmt == SBR_FMT_FASTA ? 2 : 1) + 1 + 2;  // look-back scan (+finish), match, partition
     return SBR_OK;

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(RecSource src, const Ba
                                                          const uint32_t* __restrict__ g_lens, uint32_t stride, uint32_t k,
                                                          uint16_t* __restrict__ assign, uint32_t* __restrict__ rec_off,
                                                          uint64_t* __restrict__ key_out, uint32_t* __restrict__ cnt,
-                                                         uint32_t nbins) {
+                                                         uint32_t* __restrict__ cta_cnt, uint32_t nbins) {
     extern __shared__ __align__(16) uint8_t s_mem[];
     // layout: [warps][nbins] histogram | region_base copy | table
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_mem);
@@ -205,8 +205,17 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(RecSource src, const Ba
             }
         }
     }
-    __syncwarp();
-    for (uint32_t b = lane; b < nbins; b += 32) cnt[(size_t)b * V + v] = mine[b];
+    // kernel 3's inputs: per bin, what the CTA's earlier warp slices hold (cnt) and what the whole CTA holds (cta_cnt)
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            cnt[(size_t)b * V + blockIdx.x * WARPS + w] = run;
+            run += s_hist[(size_t)w * nbins + b];
+        }
+        cta_cnt[(size_t)b * gridDim.x + blockIdx.x] = run;
+    }
 }
 
 }  // namespace
@@ -229,7 +238,7 @@ struct MatchLaunch {
     uint32_t n, m, k, stride;
     const uint8_t* text; uint32_t nbytes;
     // outputs
-    uint16_t* assign; uint32_t* rec_off; uint64_t* key_out; uint32_t* cnt; uint32_t nbins;
+    uint16_t* assign; uint32_t* rec_off; uint64_t* key_out; uint32_t* cnt; uint32_t* cta_cnt; uint32_t nbins;
     int grid;  // = the partition plan's grid: the histogram slices are kernel 3's slices
 };
 
@@ -253,13 +262,13 @@ cudaError_t match_launch(const MatchLaunch& L, cudaStream_t stream) {
     size_t smem = match_smem(L.n, L.stride, L.nbins, generic);
     if (generic)
         k_match<2><<<L.grid, MATCH_THREADS, smem, stream>>>(src, L.hdr, nullptr, L.n, L.m, 0u, nullptr, L.text, L.nbytes, L.rows,
-                                                            L.lens, L.stride, L.k, L.assign, L.rec_off, L.key_out, L.cnt, L.nbins);
+                                                            L.lens, L.stride, L.k, L.assign, L.rec_off, L.key_out, L.cnt, L.cta_cnt, L.nbins);
     else if (L.lut)
         k_match<0><<<L.grid, MATCH_THREADS, smem, stream>>>(src, L.hdr, L.tab, L.n, L.m, code_mask, L.lut, nullptr, 0u, nullptr,
-                                                            nullptr, 0u, L.k, L.assign, L.rec_off, L.key_out, L.cnt, L.nbins);
+                                                            nullptr, 0u, L.k, L.assign, L.rec_off, L.key_out, L.cnt, L.cta_cnt, L.nbins);
     else
         k_match<1><<<L.grid, MATCH_THREADS, smem, stream>>>(src, L.hdr, L.tab, L.n, L.m, code_mask, nullptr, nullptr, 0u, nullptr,
-                                                            nullptr, 0u, L.k, L.assign, L.rec_off, L.key_out, L.cnt, L.nbins);
+                                                            nullptr, 0u, L.k, L.assign, L.rec_off, L.key_out, L.cnt, L.cta_cnt, L.nbins);
     return cudaGetLastError();
 }
 

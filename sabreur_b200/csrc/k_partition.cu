@@ -8,11 +8,13 @@
 //
 // A stable counting sort over <= 65535 bins:
 //   (hist)    fused into the match kernel: every warp owns a contiguous slice of the records and counts
-//             its bins in shared memory while it writes the assignments -> cnt[bin][slice]
-//   k_binscan one block per bin: exclusive scan of cnt[bin][*] in place, bin totals -> bin_count; the last
-//             block to finish scans bin_count into bin_start
-//   k_scatter same slices; per warp a running cursor per bin in shared memory; __match_any_sync
-//             ranks equal bins inside each 32-record step so ties keep input order
+//             its bins in shared memory while it writes the assignments.  The CTA then leaves two things:
+//             cnt[bin][slice] = records of that bin in the CTA's EARLIER warp slices, and
+//             cta_cnt[bin][cta] = records of that bin in the whole CTA
+//   k_binscan one block per bin: exclusive scan of cta_cnt[bin][*] in place, bin totals -> bin_count; the
+//             last block to finish scans bin_count into bin_start
+//   k_scatter same slices; a warp's cursor for a bin starts at bin_start + cta_cnt + cnt; equal bins inside
+//             each 32-record step are ranked with one ballot per bin-index bit, so ties keep input order
 //                                                                   (reads assign again, writes 4 B/record)
 #include "sbr_common.cuh"
 
@@ -32,40 +34,46 @@ __device__ __forceinline__ void slice_range(uint32_t n, uint32_t V, uint32_t v, 
     hi = b < n ? (uint32_t)b : n;
 }
 
-// One block per bin: in-place exclusive scan over the V slices of that bin (every thread owns a contiguous
-// chunk of slices).  The last block to finish turns the bin totals into bin_start (exclusive scan over bins).
-__global__ void __launch_bounds__(PART_THREADS) k_binscan(uint32_t* __restrict__ cnt, uint32_t V, uint32_t nbins,
+// One block per bin: in-place exclusive scan over the G CTA totals of that bin (every thread owns a contiguous
+// chunk).  The last block to finish turns the bin totals into bin_start (exclusive scan over bins).
+__global__ void __launch_bounds__(PART_THREADS) k_binscan(uint32_t* __restrict__ cta_cnt, uint32_t G, uint32_t nbins,
                                                           uint32_t* __restrict__ bin_count,
                                                           uint32_t* __restrict__ bin_start /* nbins + 1 */,
                                                           uint32_t* __restrict__ done_counter) {
     __shared__ uint32_t s_warp[PART_WARPS];
     __shared__ uint32_t s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* row = cnt + (size_t)blockIdx.x * V;
-    // every warp owns a contiguous run of slices and walks it 32 at a time (coalesced)
-    const uint32_t per = (((V + PART_WARPS - 1) / PART_WARPS) + 31u) & ~31u;
-    const uint32_t w0 = min((uint32_t)warp * per, V), w1 = min(w0 + per, V);
-    uint32_t sum = 0;
-    for (uint32_t i = w0 + lane; i < w1; i += 32) sum += row[i];
-    sum = warp_sum(sum);
-    if (lane == 0) s_warp[warp] = sum;
-    __syncthreads();
-    uint32_t carry = 0, tot = 0;
+    uint32_t* row = cta_cnt + (size_t)blockIdx.x * G;
+    constexpr int CH = 8;  // entries per thread and round
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < G; base += PART_THREADS * CH) {
+        const uint32_t i0 = base + threadIdx.x * CH;
+        uint32_t x[CH], sum = 0;
 #pragma unroll
-    for (int w = 0; w < PART_WARPS; ++w) {
-        uint32_t t = s_warp[w];
-        if (w < warp) carry += t;
-        tot += t;
-    }
-    for (uint32_t i0 = w0; i0 < w1; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        const uint32_t x = i < w1 ? row[i] : 0u;
-        const uint32_t inc = warp_incl_scan(x, lane);
-        if (i < w1) row[i] = carry + inc - x;
-        carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        for (int j = 0; j < CH; ++j) {
+            x[j] = i0 + j < G ? row[i0 + j] : 0u;
+            sum += x[j];
+        }
+        const uint32_t inc = warp_incl_scan(sum, lane);
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t pre = carry + inc - sum, tot = 0;
+#pragma unroll
+        for (int w = 0; w < PART_WARPS; ++w) {
+            const uint32_t t = s_warp[w];
+            if (w < warp) pre += t;
+            tot += t;
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            if (i0 + j < G) row[i0 + j] = pre;
+            pre += x[j];
+        }
+        carry += tot;
+        __syncthreads();
     }
     if (threadIdx.x == 0) {
-        bin_count[blockIdx.x] = tot;
+        bin_count[blockIdx.x] = carry;
         __threadfence();
         s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1 ? 1u : 0u;
     }
@@ -97,20 +105,34 @@ __global__ void __launch_bounds__(PART_THREADS) k_binscan(uint32_t* __restrict__
     if (threadIdx.x == 0) bin_start[nbins] = s_carry;
 }
 
+// lanes holding the same bin as this lane, from one ballot per bit of the bin index (NBITS = bits needed for nbins;
+// dead lanes carry an index with a bit above NBITS set and fall into their own group through the extra ballot)
+__device__ __forceinline__ uint32_t same_bin_lanes(uint32_t bin, uint32_t nbits, bool live) {
+    uint32_t peers = __ballot_sync(0xFFFFFFFFu, live);
+    if (!live) peers = ~peers;
+    for (uint32_t k = 0; k < nbits; ++k) {
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, (bin >> k) & 1u);
+        peers &= ((bin >> k) & 1u) ? b : ~b;
+    }
+    return peers;
+}
+
 __global__ void __launch_bounds__(PART_THREADS) k_scatter(const uint16_t* __restrict__ assign,
-                                                          const BatchHeader* __restrict__ hdr, uint32_t nbins,
-                                                          const uint32_t* __restrict__ cnt /* scanned */,
+                                                          const BatchHeader* __restrict__ hdr, uint32_t nbins, uint32_t nbits,
+                                                          const uint32_t* __restrict__ cnt /* within-CTA exclusive */,
+                                                          const uint32_t* __restrict__ cta_cnt /* scanned over CTAs */,
                                                           const uint32_t* __restrict__ bin_start,
                                                           uint32_t* __restrict__ order) {
     extern __shared__ uint32_t s_cur[];  // [PART_WARPS][nbins] running cursor per bin
     const uint32_t n = hdr->n_records;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t V = gridDim.x * PART_WARPS, v = blockIdx.x * PART_WARPS + warp;
+    const uint32_t G = gridDim.x, V = G * PART_WARPS, v = blockIdx.x * PART_WARPS + warp;
     uint32_t* cur = s_cur + (size_t)warp * nbins;
     uint32_t lo, hi;
     slice_range(n, V, v, lo, hi);
     if (lo >= hi) return;  // warp-uniform
-    for (uint32_t b = lane; b < nbins; b += 32) cur[b] = bin_start[b] + cnt[(size_t)b * V + v];
+    for (uint32_t b = lane; b < nbins; b += 32)
+        cur[b] = bin_start[b] + cta_cnt[(size_t)b * G + blockIdx.x] + cnt[(size_t)b * V + v];
     __syncwarp();
     const uint32_t lt = (1u << lane) - 1u;
     constexpr int U = 4;  // the loads of four 32-record groups are in flight together; ranking stays in order
@@ -119,7 +141,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_scatter(const uint16_t* __rest
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t i = g0 + u * 32 + lane;
-            bins[u] = i < hi ? (uint32_t)assign[i] : 0xFFFFFFFFu;  // dead lanes form their own group
+            bins[u] = i < hi ? (uint32_t)assign[i] : 0u;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -127,15 +149,12 @@ __global__ void __launch_bounds__(PART_THREADS) k_scatter(const uint16_t* __rest
             if (g0 + u * 32 >= hi) break;  // warp-uniform
             const bool live = i < hi;
             const uint32_t bin = bins[u];
-            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, bin);
+            const uint32_t peers = same_bin_lanes(bin, nbits, live);
             const uint32_t rank = __popc(peers & lt);
-            const int leader = __ffs(peers) - 1;
-            uint32_t base = 0;
-            if (live && lane == leader) {
-                base = cur[bin];
-                cur[bin] = base + __popc(peers);
-            }
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            // every lane of a group reads the group's cursor (a broadcast), then the group's first lane advances it
+            const uint32_t base = live ? cur[bin] : 0u;
+            __syncwarp();
+            if (live && rank == 0) cur[bin] = base + __popc(peers);
             if (live) order[base + rank] = i;
             __syncwarp();
         }
@@ -145,9 +164,10 @@ __global__ void __launch_bounds__(PART_THREADS) k_scatter(const uint16_t* __rest
 }  // namespace
 
 struct PartitionPlan {
-    int grid;      // blocks of k_hist / k_scatter
+    int grid;      // blocks of the match kernel / k_scatter
     uint32_t V;    // warp slices
     size_t smem;   // dynamic shared bytes
+    uint32_t nbits;  // bits of a bin index
 };
 
 PartitionPlan partition_plan(uint32_t nbins, uint32_t max_records, int sms) {
@@ -162,6 +182,8 @@ PartitionPlan partition_plan(uint32_t nbins, uint32_t max_records, int sms) {
     p.grid = (int)max(1u, g);
     p.V = (uint32_t)p.grid * PART_WARPS;
     p.smem = smem;
+    p.nbits = 1;
+    while ((1u << p.nbits) < nbins) ++p.nbits;
     return p;
 }
 
@@ -170,10 +192,10 @@ cudaError_t partition_prepare() {
 }
 
 cudaError_t partition_launch(const uint16_t* d_assign, const BatchHeader* d_hdr, uint32_t nbins, uint32_t* d_cnt,
-                             uint32_t* d_bin_count, uint32_t* d_bin_start, uint32_t* d_order, uint32_t* d_done_counter,
-                             const PartitionPlan& p, cudaStream_t stream) {
-    k_binscan<<<nbins, PART_THREADS, 0, stream>>>(d_cnt, p.V, nbins, d_bin_count, d_bin_start, d_done_counter);
-    k_scatter<<<p.grid, PART_THREADS, p.smem, stream>>>(d_assign, d_hdr, nbins, d_cnt, d_bin_start, d_order);
+                             uint32_t* d_cta_cnt, uint32_t* d_bin_count, uint32_t* d_bin_start, uint32_t* d_order,
+                             uint32_t* d_done_counter, const PartitionPlan& p, cudaStream_t stream) {
+    k_binscan<<<nbins, PART_THREADS, 0, stream>>>(d_cta_cnt, (uint32_t)p.grid, nbins, d_bin_count, d_bin_start, d_done_counter);
+    k_scatter<<<p.grid, PART_THREADS, p.smem, stream>>>(d_assign, d_hdr, nbins, p.nbits, d_cnt, d_cta_cnt, d_bin_start, d_order);
     return cudaGetLastError();
 }
 

@@ -210,12 +210,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
     uint32_t* const wl = S.wl[warp];
     const uint32_t wl_addr = smem_u32(wl + GHOSTS);  // shared-window address of the slice's entry 0
 
+    const uint64_t text_policy = l2_evict_first_policy();
     auto issue = [&](int s, uint32_t tile) {  // thread 0 only
         uint32_t lo = tile * (uint32_t)FAST_TILE;
         uint32_t valid = min((uint32_t)FAST_TILE, A.nbytes - lo);
         uint32_t bytes = (valid + 15u) & ~15u;  // the text buffer is padded to 16 bytes
         mbar_expect_tx(&S.full_bar[s], bytes);
-        bulk_g2s(stage_buf + s * STAGE_STRIDE, A.text + lo, bytes, &S.full_bar[s]);
+        bulk_g2s_hint(stage_buf + s * STAGE_STRIDE, A.text + lo, bytes, &S.full_bar[s], text_policy);
     };
 
     if (tid == 0) {
@@ -587,7 +588,8 @@ template <int FMT>
 __global__ void __launch_bounds__(MAX_REGIONS) k_scan_finish(BatchHeader* hdr, RegionInfo* info, uint32_t n_regions,
                                                             uint32_t nbytes, uint32_t max_records, uint32_t final_batch,
                                                             uint32_t* region_base /* [n_regions+1] */,
-                                                            uint32_t* rec_off_dense) {
+                                                            uint32_t* rec_off_dense, uint4* lookback_desc,
+                                                            uint32_t n_desc) {
     __shared__ uint32_t s_nl[MAX_REGIONS], s_rec[MAX_REGIONS];
     __shared__ uint32_t s_fail, s_last_region;
     const uint32_t c = threadIdx.x;
@@ -633,6 +635,8 @@ __global__ void __launch_bounds__(MAX_REGIONS) k_scan_finish(BatchHeader* hdr, R
     if (total_rec > max_records) s_fail = 1;
     __syncthreads();
     const bool fail = s_fail != 0;
+    if (fail)  // rare: the exact scan's tile descriptors must start out zeroed (the launch path no longer memsets them)
+        for (uint32_t i = c; i < n_desc; i += MAX_REGIONS) lookback_desc[i] = make_uint4(0u, 0u, 0u, 0u);
     if (c < n_regions) region_base[c] = rec_before;
     if (c == 0) {
         region_base[n_regions] = total_rec;
@@ -726,7 +730,8 @@ cudaError_t scan_fast_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbyte
                              uint32_t n_regions, uint32_t tiles_per_region, uint32_t extra_regions, uint32_t bc_len,
                              uint32_t packed,
                              uint32_t final_batch, BatchHeader* hdr, RegionInfo* info, uint32_t* region_base,
-                             uint32_t* seg_rec_off, uint64_t* seg_key, uint32_t* rec_off_dense, cudaStream_t stream) {
+                             uint32_t* seg_rec_off, uint64_t* seg_key, uint32_t* rec_off_dense, uint4* lookback_desc,
+                             uint32_t n_desc, cudaStream_t stream) {
     FastArgs A;
     A.text = d_text;
     A.nbytes = nbytes;
@@ -751,11 +756,11 @@ cudaError_t scan_fast_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbyte
     if (fmt == SBR_FMT_FASTQ) {
         fastq_kernel(bc_len, packed)<<<n_regions, SCAN_THREADS, smem, stream>>>(A);
         k_scan_finish<SBR_FMT_FASTQ><<<1, MAX_REGIONS, 0, stream>>>(hdr, info, n_regions, nbytes, max_records, final_batch,
-                                                                    region_base, rec_off_dense);
+                                                                    region_base, rec_off_dense, lookback_desc, n_desc);
     } else {
         k_scan_fast<SBR_FMT_FASTA, 0><<<n_regions, SCAN_THREADS, smem, stream>>>(A);
         k_scan_finish<SBR_FMT_FASTA><<<1, MAX_REGIONS, 0, stream>>>(hdr, info, n_regions, nbytes, max_records, final_batch,
-                                                                    region_base, rec_off_dense);
+                                                                    region_base, rec_off_dense, lookback_desc, n_desc);
     }
     return cudaGetLastError();
 }

@@ -110,6 +110,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+// the same with an L2 eviction-priority hint: the text is read exactly once, so its lines are marked evict-first and
+// leave the (much smaller) per-record arrays the scan writes resident in L2 for the match kernel
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
 // single-copy-atomic 128-bit accesses for the look-back descriptors (SASS LDG/STG.E.128.STRONG.GPU)
 __device__ __forceinline__ uint4 ld_desc(const uint4* p) {
     uint4 v;

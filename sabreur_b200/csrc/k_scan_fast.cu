@@ -46,7 +46,10 @@ constexpr int FAST_STAGES = 2;
 // still addressable in shared memory at (stage base + position - tile start)
 constexpr int TAIL_PAD = 512;
 __host__ __device__ constexpr int stage_stride(int fmt) { return (fmt == SBR_FMT_FASTQ ? TAIL_PAD : 0) + FAST_TILE; }  // FASTA has no use for the pad
-constexpr int WL_CAP = 188;  // newline positions per warp slice held in shared memory (>= 16.4-byte lines on average)
+constexpr int WL_CAP = 188;
+constexpr int FASTA_CHUNKS = (WL_CAP + 31) / 32;
+constexpr uint32_t FASTA_START = 1u << 30;  // list entry flag: a FASTA record starts behind this newline
+constexpr uint32_t POS_MASK = FASTA_START - 1u;  // newline positions per warp slice held in shared memory (>= 16.4-byte lines on average)
 
 template <int FMT>
 struct FastSmem {
@@ -55,10 +58,10 @@ struct FastSmem {
     uint32_t wl[FAST_WARPS][GHOSTS + WL_CAP];
     uint32_t wtot[2][FAST_WARPS];           // by tile parity: newlines | record starts << 16 of each warp slice
     uint32_t wtail[2][FAST_WARPS][GHOSTS];  // by tile parity: the slice's last four newline positions, [0] most recent
+    uint32_t whead[2][FAST_WARPS][2];       // by tile parity: the slice's first two newline positions (FASTA looks ahead)
     uint32_t gh[2][GHOSTS];                 // by tile parity: the four most recent newlines before the tile
     uint32_t cnt[2];                        // newlines of the region before the tile
     uint32_t rcnt[2];                       // FASTA: record starts of the region before the tile
-    uint8_t wrl[FMT == SBR_FMT_FASTA ? FAST_WARPS : 1][FMT == SBR_FMT_FASTA ? WL_CAP + 4 : 4];  // FASTA: list index of record starts
     uint32_t first[8];  // FASTQ: the region's first eight newline positions
     uint32_t nfirst;
     uint32_t h;            // FASTQ: phase of the region's first newline
@@ -69,7 +72,7 @@ struct FastSmem {
     uint32_t fail;
     uint32_t done;         // FASTQ: the record open at the region's end has been finished
     uint32_t crlf;
-    unsigned long long last_start;  // FASTA: (newlines up to the one before the last record start) << 32 | its offset
+    unsigned long long wlast[FAST_WARPS];  // FASTA, per warp: (newlines up to the one before its last record start) << 32 | offset
 };
 
 struct FastArgs {
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
         for (int w = 0; w < FAST_WARPS; ++w) S.wmax[w][0] = S.wmax[w][1] = 0;
         S.fail = 0;
         S.done = 0;
-        S.last_start = 0;
+        for (int w = 0; w < FAST_WARPS; ++w) S.wlast[w] = 0;
         S.crlf = 0;
         // "the newline before the region": a record whose final newline is the region's fourth starts at region_lo
         S.gh[0][0] = region_lo - 1u;  // == NOPOS for region 0
@@ -271,38 +274,20 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
         const uint8_t* sm = stage_buf + s * STAGE_STRIDE;
         mbar_wait(&S.full_bar[s], parity);
 
-        // ---- newline (and '>') masks of this lane's 48 bytes in each unit of the warp's slice ----------
+        // ---- newline masks of this lane's 48 bytes in each unit of the warp's slice ---------------------
         const uint32_t woff = (uint32_t)warp * WARP_SLICE + (uint32_t)lane * SCAN_BYTES_PER_THREAD;
-        uint32_t m_lo[FAST_UNITS], m_hi[FAST_UNITS], r_lo[FAST_UNITS], r_hi[FAST_UNITS];
-        uint32_t cn2 = 0, cr2 = 0;  // per-unit counts, 16 bits each
+        uint32_t m_lo[FAST_UNITS], m_hi[FAST_UNITS];
+        uint32_t cn2 = 0;  // per-unit counts, 16 bits each
 #pragma unroll
         for (int j = 0; j < FAST_UNITS; ++j) {
             const uint32_t uoff = woff + j * UNIT_BYTES;
             const uint4* src = reinterpret_cast<const uint4*>(sm + uoff);
             const uint4 v0 = src[0], v1 = src[1], v2 = src[2];
             eq_mask48(v0, v1, v2, c7f, c0a, c80, m_lo[j], m_hi[j]);
-            uint32_t vm_lo = 0xFFFFFFFFu, vm_hi = 0xFFFFu;
             if (uoff + SCAN_BYTES_PER_THREAD > valid) {
                 uint32_t nv = valid > uoff ? valid - uoff : 0u;
-                vm_lo = nv >= 32 ? 0xFFFFFFFFu : ((1u << nv) - 1u);
-                vm_hi = nv > 32 ? ((1u << (nv - 32)) - 1u) : 0u;
-                m_lo[j] &= vm_lo;
-                m_hi[j] &= vm_hi;
-            }
-            r_lo[j] = r_hi[j] = 0;
-            if (FMT == SBR_FMT_FASTA) {
-                uint32_t g_lo, g_hi;
-                eq_mask48(v0, v1, v2, c7f, A.c3e, c80, g_lo, g_hi);
-                g_lo &= vm_lo;
-                g_hi &= vm_hi;
-                const uint32_t nxt = uoff + SCAN_BYTES_PER_THREAD;
-                uint32_t nb = 0;
-                if (nxt < valid) nb = sm[nxt];
-                else if (nxt == (uint32_t)FAST_TILE && lo + nxt < A.nbytes) nb = A.text[lo + nxt];
-                // a record starts after every '\n' that is followed by '>'
-                r_lo[j] = m_lo[j] & ((g_lo >> 1) | (g_hi << 31));
-                r_hi[j] = m_hi[j] & ((g_hi >> 1) | (nb == '>' ? 0x8000u : 0u));
-                cr2 |= (uint32_t)(__popc(r_lo[j]) + __popc(r_hi[j])) << (16 * j);
+                m_lo[j] &= nv >= 32 ? 0xFFFFFFFFu : ((1u << nv) - 1u);
+                m_hi[j] &= nv > 32 ? ((1u << (nv - 32)) - 1u) : 0u;
             }
             cn2 |= (uint32_t)(__popc(m_lo[j]) + __popc(m_hi[j])) << (16 * j);
         }
@@ -310,47 +295,56 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
         const uint32_t tot_n = __shfl_sync(0xFFFFFFFFu, incl_n, 31);
         const uint32_t ex_n = incl_n - cn2;
         const uint32_t n0 = tot_n & 0xFFFFu, n_w = n0 + (tot_n >> 16);  // newlines of unit 0 / of the whole slice
-        uint32_t nr0 = 0, nr_w = 0, ex_r = 0;
-        if (FMT == SBR_FMT_FASTA) {
-            const uint32_t incl_r = warp_incl_scan(cr2, lane);
-            const uint32_t tot_r = __shfl_sync(0xFFFFFFFFu, incl_r, 31);
-            ex_r = incl_r - cr2;
-            nr0 = tot_r & 0xFFFFu;
-            nr_w = nr0 + (tot_r >> 16);
-        }
+        uint32_t nr_w = 0;  // FASTA: record starts of the slice
         // read before the barrier: thread 0 may flip it right after that barrier, and every thread has to take
         // the same decision about the extra barrier below
         const bool was_synced = S.synced != 0;
         const bool fits = n_w <= (uint32_t)WL_CAP;  // warp-uniform
 
         // ---- compact the slice's newline positions (ascending) into the warp's list ---------------------
+        // FASTA entries also carry FASTA_START (bit 30: positions are below 2^30) when the next byte is '>', i.e. when
+        // a record starts right after the newline
+        uint32_t start_bal[FASTA_CHUNKS] = {};  // FASTA: per 32 list entries, which ones are record starts
         if (fits) {
             bool crlf = false;
+            const uint32_t sm_a = smem_u32(sm);
 #pragma unroll
             for (int j = 0; j < FAST_UNITS; ++j) {
                 const uint32_t idx = j ? n0 + (ex_n >> 16) : (ex_n & 0xFFFFu);
-                uint32_t rk = j ? nr0 + (ex_r >> 16) : (ex_r & 0xFFFFu);
                 uint32_t a = wl_addr + 4u * idx;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t mm = half ? m_hi[j] : m_lo[j];
-                    const uint32_t rr = half ? r_hi[j] : r_lo[j];
                     const uint32_t o0 = woff + j * UNIT_BYTES + 32 * half;
                     const uint32_t pos0 = lo + o0;
                     while (mm) {
                         const uint32_t b = __ffs(mm) - 1;
                         mm &= mm - 1;
-                        sts_u32(a, pos0 + b);
+                        uint32_t entry = pos0 + b;
                         if (FMT == SBR_FMT_FASTA) {
-                            if ((rr >> b) & 1u) S.wrl[warp][rk++] = (uint8_t)((a - wl_addr) >> 2);
-                            const uint32_t o = o0 + b;  // CR before LF makes a FASTA batch non-canonical
-                            crlf |= o > 0 ? sm[o - 1] == '\r' : (lo > 0 && A.text[lo - 1] == '\r');
+                            const uint32_t o = o0 + b;
+                            uint32_t nxt = 0;  // the byte behind the newline
+                            if (o + 1 < valid) nxt = lds_u8(sm_a + o + 1);
+                            else if (lo + o + 1 < A.nbytes) nxt = A.text[lo + o + 1];
+                            if (nxt == '>') entry |= FASTA_START;
+                            // CR before LF makes a FASTA batch non-canonical
+                            crlf |= o > 0 ? lds_u8(sm_a + o - 1) == '\r' : (lo > 0 && A.text[lo - 1] == '\r');
                         }
+                        sts_u32(a, entry);
                         a += 4u;
                     }
                 }
             }
-            if (FMT == SBR_FMT_FASTA && crlf) S.crlf = 1;
+            if (FMT == SBR_FMT_FASTA) {
+                if (crlf) S.crlf = 1;
+                __syncwarp();
+#pragma unroll
+                for (int ch = 0; ch < FASTA_CHUNKS; ++ch) {
+                    const uint32_t jx = ch * 32 + lane;
+                    start_bal[ch] = __ballot_sync(0xFFFFFFFFu, jx < n_w && (wl[GHOSTS + jx] & FASTA_START));
+                    nr_w += __popc(start_bal[ch]);
+                }
+            }
         } else if (lane == 0) {
             S.fail = 1;  // newline-dense slice: the exact scan's job
         }
@@ -360,6 +354,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
             const uint32_t nn = fits ? n_w : 0u;
             S.wtail[par][warp][lane] = nn > (uint32_t)lane ? wl[GHOSTS + nn - 1 - lane] : NOPOS;
             if (lane == 0) S.wtot[par][warp] = n_w | (nr_w << 16);
+            if (FMT == SBR_FMT_FASTA && lane < 2) S.whead[par][warp][lane] = nn > (uint32_t)lane ? (wl[GHOSTS + lane] & POS_MASK) : NOPOS;
         }
         __syncthreads();  // the tile's barrier
         if (tid == 0 && it >= 1 && !overrun) {  // tile it-1 is finished by everybody: refill its stage
@@ -533,30 +528,57 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
                 }
             }
         } else {
-            // ---- FASTA: lane u handles the u-th record start of the slice ------------------------------
+            // ---- FASTA: every list entry flagged as a record start is one record; its lane evaluates it -------
             const ByteSrc B{sm, A.text, lo, lo + valid};
-            const uint32_t rbase = S.rcnt[par] + pre_r;  // starts seen before this slice (record 0 of the batch not counted)
-            const uint32_t own_first = (c == 0) ? 1u : 0u;
-            for (uint32_t u = (uint32_t)lane; u < nr_w && fits; u += 32u) {  // dense slices already failed
-                const uint32_t idx = S.wrl[warp][u];
-                const uint32_t p = wl[GHOSTS + idx];
-                const uint32_t hint = (idx + 1 < n_w) ? wl[GHOSTS + idx + 1] : NOPOS;
-                uint64_t key;
-                const uint32_t why = fasta_eval(B, A.nbytes, p + 1, hint, A.bc_len, A.packed, key);
-                const uint32_t rl = rbase + u + own_first;
-                // a prefix cut by the end of a non-final batch belongs to the incomplete last record: no error
-                if (rl >= A.cap_r || why == 1 || (why == 2 && A.final_batch)) S.fail = 1;
-                else {
-                    A.seg_rec_off[(size_t)c * A.cap_r + rl] = p + 1;
-                    A.seg_key[(size_t)c * A.cap_r + rl] = key;
+            const uint32_t rbase = S.rcnt[par] + pre_r + ((c == 0) ? 1u : 0u);  // records before this slice (record 0 of the batch counted)
+            const uint32_t sbase = smem_u32(sm) - lo;  // shared-window address of batch position 0 (wraps)
+            uint32_t u0 = 0;  // starts in earlier chunks of the slice
+#pragma unroll
+            for (int ch = 0; ch < FASTA_CHUNKS; ++ch) {
+                if (!fits || ch * 32 >= (int)n_w) break;  // warp-uniform
+                const uint32_t bal = start_bal[ch];
+                if ((bal >> lane) & 1u) {
+                    const uint32_t idx = ch * 32 + lane;
+                    const uint32_t u = u0 + __popc(bal & ((1u << lane) - 1u));
+                    const uint32_t p = wl[GHOSTS + idx] & POS_MASK;
+                    // the two newlines behind the record start (the header's, the first sequence line's): from the own
+                    // list, or from the head the next slice published
+                    auto ahead = [&](uint32_t j) -> uint32_t {
+                        if (j < n_w) return wl[GHOSTS + j] & POS_MASK;
+                        return (warp + 1 < FAST_WARPS && j - n_w < 2) ? S.whead[par][warp + 1][j - n_w] : NOPOS;
+                    };
+                    const uint32_t hend = ahead(idx + 1);  // the header's newline
+                    uint64_t key = 0;
+                    uint32_t why = 3;  // 3: not decided by the fast path
+                    // single-line prefix made of A/C/G/T only, staged: pack it straight from shared memory (a newline,
+                    // CR, N ... inside the window shows up as an invalid base and sends the record to the general path)
+                    if (KW && hend != NOPOS && hend + 1 + 4 * (KW ? KW : 1) + 8 < lo + valid) {
+                        key = pack_prefix_vec<(KW ? KW : 1)>(sbase + hend + 1, A.code_mask, A.inval_mask);
+                        // all A/C/G/T: no line end can hide in the window.  Otherwise (an N, say) the window must be
+                        // known to lie on the first sequence line: the next newline is listed and far enough
+                        if ((key >> 32) == 0) why = 0;
+                        else {
+                            const uint32_t e2 = ahead(idx + 2);
+                            if (e2 != NOPOS && e2 > hend + A.bc_len) why = 0;
+                        }
+                    }
+                    if (why == 3) why = fasta_eval(B, A.nbytes, p + 1, hend, A.bc_len, A.packed, key);
+                    const uint32_t rl = rbase + u;
+                    // a prefix cut by the end of a non-final batch belongs to the incomplete last record: no error
+                    if (rl >= A.cap_r || why == 1 || (why == 2 && A.final_batch)) S.fail = 1;
+                    else {
+                        seg_off_c[rl] = p + 1;
+                        seg_key_c[rl] = key;
+                    }
+                    if (u == nr_w - 1)  // ascending over the tiles: a plain store per warp, the maximum is taken at the end
+                        S.wlast[warp] = ((unsigned long long)(base + pre_n + idx + 1) << 32) | (unsigned long long)(p + 1);
                 }
-                if (u == nr_w - 1)
-                    atomicMax(&S.last_start, ((unsigned long long)(base + pre_n + idx + 1) << 32) | (unsigned long long)(p + 1));
+                u0 += __popc(bal);
             }
             if (tid == 0 && c == 0 && it == 0) {
                 uint64_t key;
                 if (B(0) != '>') S.fail = 1;
-                const uint32_t why = fasta_eval(B, A.nbytes, 0u, (fits && n_w > 0) ? wl[GHOSTS] : NOPOS, A.bc_len, A.packed, key);
+                const uint32_t why = fasta_eval(B, A.nbytes, 0u, (fits && n_w > 0) ? (wl[GHOSTS] & POS_MASK) : NOPOS, A.bc_len, A.packed, key);
                 if (why == 1 || (why == 2 && A.final_batch)) S.fail = 1;
                 A.seg_rec_off[0] = 0;
                 A.seg_key[0] = key;
@@ -574,8 +596,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
         e.nrec = (FMT == SBR_FMT_FASTA) ? S.rcnt[n_it & 1u] + (c == 0 ? 1u : 0u) : nrec;
         e.phase = (FMT == SBR_FMT_FASTQ && S.synced) ? S.h : PHASE_UNKNOWN;
         e.flags = S.fail ? 1u : 0u;
-        e.last_start_nl = (uint32_t)(S.last_start >> 32);
-        e.last_start_off = (uint32_t)S.last_start;
+        unsigned long long last_start = 0;
+        for (int w = 0; w < FAST_WARPS; ++w) last_start = max(last_start, S.wlast[w]);
+        e.last_start_nl = (uint32_t)(last_start >> 32);
+        e.last_start_off = (uint32_t)last_start;
         e.pad[0] = e.pad[1] = 0;
         A.info[c] = e;
         if (last_end) atomicMax(&A.hdr->consumed, last_end);
@@ -671,42 +695,37 @@ size_t scan_fast_smem_bytes(uint32_t fmt) {
 }
 
 using FastKernel = void (*)(FastArgs);
-// FASTQ kernels are specialised on the number of text words covering the match window
-static FastKernel fastq_kernel(uint32_t bc_len, uint32_t packed) {
-    if (!packed) return k_scan_fast<SBR_FMT_FASTQ, 0>;
+// the kernels are specialised on the number of text words covering the match window
+template <int FMT>
+static FastKernel fast_kernel(uint32_t bc_len, uint32_t packed) {
+    if (!packed) return k_scan_fast<FMT, 0>;
     switch ((bc_len + 3) / 4) {
-        case 1: return k_scan_fast<SBR_FMT_FASTQ, 1>;
-        case 2: return k_scan_fast<SBR_FMT_FASTQ, 2>;
-        case 3: return k_scan_fast<SBR_FMT_FASTQ, 3>;
-        default: return k_scan_fast<SBR_FMT_FASTQ, 4>;
+        case 1: return k_scan_fast<FMT, 1>;
+        case 2: return k_scan_fast<FMT, 2>;
+        case 3: return k_scan_fast<FMT, 3>;
+        default: return k_scan_fast<FMT, 4>;
     }
 }
 
 cudaError_t scan_fast_prepare(int device, int* grid_fastq, int* grid_fasta) {
     cudaError_t e;
-    const FastKernel all[] = {k_scan_fast<SBR_FMT_FASTQ, 0>, k_scan_fast<SBR_FMT_FASTQ, 1>, k_scan_fast<SBR_FMT_FASTQ, 2>,
-                              k_scan_fast<SBR_FMT_FASTQ, 3>, k_scan_fast<SBR_FMT_FASTQ, 4>};
-    for (FastKernel k : all)
-        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)scan_fast_smem_bytes(SBR_FMT_FASTQ))) != cudaSuccess)
-            return e;
-    if ((e = cudaFuncSetAttribute(k_scan_fast<SBR_FMT_FASTA, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)scan_fast_smem_bytes(SBR_FMT_FASTA))) != cudaSuccess)
-        return e;
-    int sms = 0, q = 1 << 30, a = 0;
+    int sms = 0;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return e;
-    for (FastKernel k : all) {  // one grid for every FASTQ variant: the smallest residency
-        int qq = 0;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&qq, k, SCAN_THREADS, scan_fast_smem_bytes(SBR_FMT_FASTQ))) !=
-            cudaSuccess)
-            return e;
-        q = qq < q ? qq : q;
-    }
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_scan_fast<SBR_FMT_FASTA, 0>, SCAN_THREADS,
-                                                           scan_fast_smem_bytes(SBR_FMT_FASTA))) != cudaSuccess)
-        return e;
-    q = (q < 1 ? 1 : q) * sms;
-    a = (a < 1 ? 1 : a) * sms;
+    int resident[2] = {1 << 30, 1 << 30};  // FASTA, FASTQ: one grid for every variant of a format, the smallest residency
+    for (uint32_t fmt = SBR_FMT_FASTA; fmt <= SBR_FMT_FASTQ; ++fmt)
+        for (uint32_t kw = 0; kw <= 4; ++kw) {
+            const FastKernel k = fmt == SBR_FMT_FASTA ? fast_kernel<SBR_FMT_FASTA>(4 * kw, kw ? 1u : 0u)
+                                                     : fast_kernel<SBR_FMT_FASTQ>(4 * kw, kw ? 1u : 0u);
+            if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_fast_smem_bytes(fmt))) !=
+                cudaSuccess)
+                return e;
+            int r = 0;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k, SCAN_THREADS, scan_fast_smem_bytes(fmt))) != cudaSuccess)
+                return e;
+            int& best = resident[fmt - SBR_FMT_FASTA];
+            best = r < best ? r : best;
+        }
+    const int a = (resident[0] < 1 ? 1 : resident[0]) * sms, q = (resident[1] < 1 ? 1 : resident[1]) * sms;
     *grid_fastq = q > MAX_REGIONS ? MAX_REGIONS : q;
     *grid_fasta = a > MAX_REGIONS ? MAX_REGIONS : a;
     return cudaSuccess;
@@ -754,11 +773,11 @@ cudaError_t scan_fast_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbyte
     A.seg_key = seg_key;
     size_t smem = scan_fast_smem_bytes(fmt);
     if (fmt == SBR_FMT_FASTQ) {
-        fastq_kernel(bc_len, packed)<<<n_regions, SCAN_THREADS, smem, stream>>>(A);
+        fast_kernel<SBR_FMT_FASTQ>(bc_len, packed)<<<n_regions, SCAN_THREADS, smem, stream>>>(A);
         k_scan_finish<SBR_FMT_FASTQ><<<1, MAX_REGIONS, 0, stream>>>(hdr, info, n_regions, nbytes, max_records, final_batch,
                                                                     region_base, rec_off_dense, lookback_desc, n_desc);
     } else {
-        k_scan_fast<SBR_FMT_FASTA, 0><<<n_regions, SCAN_THREADS, smem, stream>>>(A);
+        fast_kernel<SBR_FMT_FASTA>(bc_len, packed)<<<n_regions, SCAN_THREADS, smem, stream>>>(A);
         k_scan_finish<SBR_FMT_FASTA><<<1, MAX_REGIONS, 0, stream>>>(hdr, info, n_regions, nbytes, max_records, final_batch,
                                                                     region_base, rec_off_dense, lookback_desc, n_desc);
     }

@@ -34,7 +34,7 @@ struct MatchLaunch {
     const uint2* tab; const uint16_t* lut; const uint8_t* rows; const uint32_t* lens;
     uint32_t n, m, k, stride;
     const uint8_t* text; uint32_t nbytes;
-    uint16_t* assign; uint32_t* rec_off; uint64_t* key_out; uint32_t* cnt; uint32_t* cta_cnt; uint32_t nbins;
+    uint16_t* assign; uint32_t* rec_off; uint64_t* key_out; uint32_t* cta_cnt; uint32_t nbins;
     int grid;
 };
 size_t match_smem(uint32_t n, uint32_t stride, uint32_t nbins, bool generic);
@@ -50,7 +50,7 @@ struct PartitionPlan {
 };
 PartitionPlan partition_plan(uint32_t nbins, uint32_t max_records, int sms);
 cudaError_t partition_prepare();
-cudaError_t partition_launch(const uint16_t* d_assign, const BatchHeader* d_hdr, uint32_t nbins, uint32_t* d_cnt,
+cudaError_t partition_launch(const uint16_t* d_assign, const BatchHeader* d_hdr, uint32_t nbins,
                              uint32_t* d_cta_cnt, uint32_t* d_bin_count, uint32_t* d_bin_start, uint32_t* d_order,
                              uint32_t* d_done_counter, const PartitionPlan& p, cudaStream_t stream);
 }  // namespace sbr
@@ -73,7 +73,6 @@ struct Slot {
     uint32_t* d_rec_off = nullptr;
     uint64_t* d_key = nullptr;
     uint16_t* d_assign = nullptr;
-    uint32_t* d_cnt = nullptr;
     uint32_t* d_cta_cnt = nullptr;
     uint32_t* d_bin_count = nullptr;
     uint32_t* d_bin_start = nullptr;
@@ -173,7 +172,7 @@ static void free_slot(Slot& s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFree(s.d_text); cudaFree(s.d_hdr); cudaFree(s.d_desc); cudaFree(s.d_rec_off); cudaFree(s.d_key);
     cudaFree(s.d_done); cudaFree(s.d_info); cudaFree(s.d_region_base); cudaFree(s.d_seg_rec_off); cudaFree(s.d_seg_key);
-    cudaFree(s.d_assign); cudaFree(s.d_cnt); cudaFree(s.d_cta_cnt); cudaFree(s.d_bin_count); cudaFree(s.d_bin_start); cudaFree(s.d_order);
+    cudaFree(s.d_assign); cudaFree(s.d_cta_cnt); cudaFree(s.d_bin_count); cudaFree(s.d_bin_start); cudaFree(s.d_order);
     cudaFreeHost(s.h_text); cudaFreeHost(s.h_hdr); cudaFreeHost(s.h_rec_off); cudaFreeHost(s.h_key);
     cudaFreeHost(s.h_assign); cudaFreeHost(s.h_bin_count); cudaFreeHost(s.h_bin_start); cudaFreeHost(s.h_order);
     if (s.hdr_ready) cudaEventDestroy(s.hdr_ready);
@@ -276,7 +275,6 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
         CU(c, cudaMalloc(&s.d_rec_off, (mr + 1) * sizeof(uint32_t)));
         CU(c, cudaMalloc(&s.d_key, (mr + 4) * sizeof(uint64_t)));
         CU(c, cudaMalloc(&s.d_assign, (mr + 4) * sizeof(uint16_t)));
-        CU(c, cudaMalloc(&s.d_cnt, (size_t)c->nbins * c->plan.V * sizeof(uint32_t)));
         CU(c, cudaMalloc(&s.d_cta_cnt, (size_t)c->nbins * c->plan.grid * sizeof(uint32_t)));
         CU(c, cudaMalloc(&s.d_bin_count, c->nbins * sizeof(uint32_t)));
         CU(c, cudaMalloc(&s.d_bin_start, (c->nbins + 1) * sizeof(uint32_t)));
@@ -374,12 +372,12 @@ static int launch_pipeline(sbr_ctx* c, Slot& s, const uint8_t* d_text, uint32_t 
         L.tab = c->packed ? c->d_tab : nullptr; L.lut = c->d_lut; L.rows = c->d_rows; L.lens = c->d_lens;
         L.n = c->cfg.n_barcodes; L.m = c->cfg.mismatch; L.k = c->cfg.bc_len; L.stride = c->cfg.bc_len;
         L.text = d_text; L.nbytes = nbytes;
-        L.assign = s.d_assign; L.rec_off = s.d_rec_off; L.key_out = s.d_key; L.cnt = s.d_cnt; L.cta_cnt = s.d_cta_cnt; L.nbins = c->nbins;
+        L.assign = s.d_assign; L.rec_off = s.d_rec_off; L.key_out = s.d_key; L.cta_cnt = s.d_cta_cnt; L.nbins = c->nbins;
         L.grid = c->plan.grid;
         CU(c, match_launch(L, st));
     }
     if (ev) CU(c, cudaEventRecord(ev[2], st));
-    CU(c, partition_launch(s.d_assign, s.d_hdr, c->nbins, s.d_cnt, s.d_cta_cnt, s.d_bin_count, s.d_bin_start, s.d_order,
+    CU(c, partition_launch(s.d_assign, s.d_hdr, c->nbins, s.d_cta_cnt, s.d_bin_count, s.d_bin_start, s.d_order,
                            s.d_done, c->plan, st));
     if (ev) CU(c, cudaEventRecord(ev[3], st));
     c->launches += (fmt == SBR_FMT_FASTA ? 2 : 1) + 1 + 2;  // look-back scan (+finish), match, partition

@@ -71,7 +71,7 @@ __device__ __forceinline__ void slice_range(uint32_t n, uint32_t V, uint32_t v, 
 // MODE 0: first-match LUT, 1: XOR+popc table walk, 2: byte-exact compare on the raw text.
 // Every warp owns a contiguous slice of the batch's records (the slices of kernel 3): it reads the
 // scan words (compacting the fast scan's per-region segments into the dense rec_off array on the way),
-// writes the assignments and counts its bins in shared memory -> cnt[bin][slice].
+// writes the assignments and counts its bins in shared memory -> cta_cnt[bin][cta].
 template <int MODE>
 __global__ void __launch_bounds__(MATCH_THREADS) k_match(RecSource src, const BatchHeader* __restrict__ hdr,
                                                          const uint2* __restrict__ g_tab, uint32_t n, uint32_t m,
@@ -80,8 +80,8 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(RecSource src, const Ba
                                                          const uint8_t* __restrict__ g_rows,
                                                          const uint32_t* __restrict__ g_lens, uint32_t stride, uint32_t k,
                                                          uint16_t* __restrict__ assign, uint32_t* __restrict__ rec_off,
-                                                         uint64_t* __restrict__ key_out, uint32_t* __restrict__ cnt,
-                                                         uint32_t* __restrict__ cta_cnt, uint32_t nbins) {
+                                                         uint64_t* __restrict__ key_out, uint32_t* __restrict__ cta_cnt,
+                                                         uint32_t nbins) {
     extern __shared__ __align__(16) uint8_t s_mem[];
     // layout: [warps][nbins] histogram | region_base copy | table
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_mem);
@@ -205,15 +205,12 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(RecSource src, const Ba
             }
         }
     }
-    // kernel 3's inputs: per bin, what the CTA's earlier warp slices hold (cnt) and what the whole CTA holds (cta_cnt)
+    // kernel 3's input: per bin, how many records the whole CTA holds
     __syncthreads();
     for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) {
         uint32_t run = 0;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            cnt[(size_t)b * V + blockIdx.x * WARPS + w] = run;
-            run += s_hist[(size_t)w * nbins + b];
-        }
+        for (int w = 0; w < WARPS; ++w) run += s_hist[(size_t)w * nbins + b];
         cta_cnt[(size_t)b * gridDim.x + blockIdx.x] = run;
     }
 }
@@ -238,7 +235,7 @@ struct MatchLaunch {
     uint32_t n, m, k, stride;
     const uint8_t* text; uint32_t nbytes;
     // outputs
-    uint16_t* assign; uint32_t* rec_off; uint64_t* key_out; uint32_t* cnt; uint32_t* cta_cnt; uint32_t nbins;
+    uint16_t* assign; uint32_t* rec_off; uint64_t* key_out; uint32_t* cta_cnt; uint32_t nbins;
     int grid;  // = the partition plan's grid: the histogram slices are kernel 3's slices
 };
 
@@ -262,13 +259,13 @@ cudaError_t match_launch(const MatchLaunch& L, cudaStream_t stream) {
     size_t smem = match_smem(L.n, L.stride, L.nbins, generic);
     if (generic)
         k_match<2><<<L.grid, MATCH_THREADS, smem, stream>>>(src, L.hdr, nullptr, L.n, L.m, 0u, nullptr, L.text, L.nbytes, L.rows,
-                                                            L.lens, L.stride, L.k, L.assign, L.rec_off, L.key_out, L.cnt, L.cta_cnt, L.nbins);
+                                                            L.lens, L.stride, L.k, L.assign, L.rec_off, L.key_out, L.cta_cnt, L.nbins);
     else if (L.lut)
         k_match<0><<<L.grid, MATCH_THREADS, smem, stream>>>(src, L.hdr, L.tab, L.n, L.m, code_mask, L.lut, nullptr, 0u, nullptr,
-                                                            nullptr, 0u, L.k, L.assign, L.rec_off, L.key_out, L.cnt, L.cta_cnt, L.nbins);
+                                                            nullptr, 0u, L.k, L.assign, L.rec_off, L.key_out, L.cta_cnt, L.nbins);
     else
         k_match<1><<<L.grid, MATCH_THREADS, smem, stream>>>(src, L.hdr, L.tab, L.n, L.m, code_mask, nullptr, nullptr, 0u, nullptr,
-                                                            nullptr, 0u, L.k, L.assign, L.rec_off, L.key_out, L.cnt, L.cta_cnt, L.nbins);
+                                                            nullptr, 0u, L.k, L.assign, L.rec_off, L.key_out, L.cta_cnt, L.nbins);
     return cudaGetLastError();
 }
 

@@ -8,14 +8,14 @@
 //
 // A stable counting sort over <= 65535 bins:
 //   (hist)    fused into the match kernel: every warp owns a contiguous slice of the records and counts
-//             its bins in shared memory while it writes the assignments.  The CTA then leaves two things:
-//             cnt[bin][slice] = records of that bin in the CTA's EARLIER warp slices, and
-//             cta_cnt[bin][cta] = records of that bin in the whole CTA
+//             its bins in shared memory while it writes the assignments; the CTA leaves
+//             cta_cnt[bin][cta] = records of that bin in the whole CTA (8 consecutive warp slices)
 //   k_binscan one block per bin: exclusive scan of cta_cnt[bin][*] in place, bin totals -> bin_count; the
 //             last block to finish scans bin_count into bin_start
-//   k_scatter same slices; a warp's cursor for a bin starts at bin_start + cta_cnt + cnt; equal bins inside
-//             each 32-record step are ranked with one ballot per bin-index bit, so ties keep input order
-//                                                                   (reads assign again, writes 4 B/record)
+//   k_scatter same slices.  The CTA first recounts its warps' bins in shared memory (assign is L2-resident) and
+//             turns them into cursors: bin_start + cta_cnt + what the CTA's earlier warps hold.  Equal bins
+//             inside each 32-record step are ranked with one ballot per bin-index bit, so ties keep input order
+//                                                                   (reads assign twice, writes 4 B/record)
 #include "sbr_common.cuh"
 
 namespace sbr {
@@ -119,21 +119,31 @@ __device__ __forceinline__ uint32_t same_bin_lanes(uint32_t bin, uint32_t nbits,
 
 __global__ void __launch_bounds__(PART_THREADS) k_scatter(const uint16_t* __restrict__ assign,
                                                           const BatchHeader* __restrict__ hdr, uint32_t nbins, uint32_t nbits,
-                                                          const uint32_t* __restrict__ cnt /* within-CTA exclusive */,
                                                           const uint32_t* __restrict__ cta_cnt /* scanned over CTAs */,
                                                           const uint32_t* __restrict__ bin_start,
                                                           uint32_t* __restrict__ order) {
-    extern __shared__ uint32_t s_cur[];  // [PART_WARPS][nbins] running cursor per bin
+    extern __shared__ uint32_t s_cur[];  // [PART_WARPS][nbins]: counts first, then the running cursor per bin
     const uint32_t n = hdr->n_records;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t G = gridDim.x, V = G * PART_WARPS, v = blockIdx.x * PART_WARPS + warp;
     uint32_t* cur = s_cur + (size_t)warp * nbins;
     uint32_t lo, hi;
     slice_range(n, V, v, lo, hi);
+    for (uint32_t i = threadIdx.x; i < PART_WARPS * nbins; i += PART_THREADS) s_cur[i] = 0;
+    __syncthreads();
+    for (uint32_t i = lo + lane; i < hi; i += 32) atomicAdd(&cur[assign[i]], 1u);
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nbins; b += PART_THREADS) {
+        uint32_t run = bin_start[b] + cta_cnt[(size_t)b * G + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < PART_WARPS; ++w) {
+            const uint32_t t = s_cur[(size_t)w * nbins + b];
+            s_cur[(size_t)w * nbins + b] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
     if (lo >= hi) return;  // warp-uniform
-    for (uint32_t b = lane; b < nbins; b += 32)
-        cur[b] = bin_start[b] + cta_cnt[(size_t)b * G + blockIdx.x] + cnt[(size_t)b * V + v];
-    __syncwarp();
     const uint32_t lt = (1u << lane) - 1u;
     constexpr int U = 4;  // the loads of four 32-record groups are in flight together; ranking stays in order
     for (uint32_t g0 = lo; g0 < hi; g0 += 32 * U) {
@@ -176,9 +186,7 @@ PartitionPlan partition_plan(uint32_t nbins, uint32_t max_records, int sms) {
     size_t fit = (200 * 1024) / (smem ? smem : 1);
     int per_sm = fit < 1 ? 1 : (fit > 8 ? 8 : (int)fit);
     uint32_t want = (max_records + PART_THREADS * 4 - 1) / (PART_THREADS * 4);  // >= 4 steps of 32 per warp
-    uint32_t cap_mem = ((2u << 20) / nbins) / PART_WARPS;  // keep cnt[nbins][V] around 8 MB
     uint32_t g = min(want, (uint32_t)(sms * per_sm));
-    g = min(g, max(cap_mem, (uint32_t)sms));
     p.grid = (int)max(1u, g);
     p.V = (uint32_t)p.grid * PART_WARPS;
     p.smem = smem;
@@ -191,11 +199,11 @@ cudaError_t partition_prepare() {
     return cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 }
 
-cudaError_t partition_launch(const uint16_t* d_assign, const BatchHeader* d_hdr, uint32_t nbins, uint32_t* d_cnt,
+cudaError_t partition_launch(const uint16_t* d_assign, const BatchHeader* d_hdr, uint32_t nbins,
                              uint32_t* d_cta_cnt, uint32_t* d_bin_count, uint32_t* d_bin_start, uint32_t* d_order,
                              uint32_t* d_done_counter, const PartitionPlan& p, cudaStream_t stream) {
     k_binscan<<<nbins, PART_THREADS, 0, stream>>>(d_cta_cnt, (uint32_t)p.grid, nbins, d_bin_count, d_bin_start, d_done_counter);
-    k_scatter<<<p.grid, PART_THREADS, p.smem, stream>>>(d_assign, d_hdr, nbins, p.nbits, d_cnt, d_cta_cnt, d_bin_start, d_order);
+    k_scatter<<<p.grid, PART_THREADS, p.smem, stream>>>(d_assign, d_hdr, nbins, p.nbits, d_cta_cnt, d_bin_start, d_order);
     return cudaGetLastError();
 }
 

@@ -62,6 +62,7 @@ typedef enum {
                                   the table holds non-ACGT bytes or bc_len > 16) */
 #define SBR_CFG_TIMING   0x4u  /* record CUDA events around every kernel: see sbr_timing_collect() */
 #define SBR_CFG_EXACT_SCAN 0x8u /* skip the region-parallel scan: always run the look-back scan */
+#define SBR_CFG_NO_FUSE 0x10u   /* run match and partition as separate launches (default: one cooperative launch) */
 
 typedef struct sbr_ctx sbr_ctx;
 

@@ -12,7 +12,7 @@ SBR_OK = 0
 ST_INVALID_START, ST_INVALID_SEP, ST_UNEQUAL_LEN, ST_SHORT_READ = 0x01, 0x02, 0x04, 0x08
 ST_TRUNCATED, ST_REC_OVERFLOW, ST_NONCANONICAL, ST_ERROR_MASK = 0x10, 0x20, 0x40, 0x1F
 FMT_AUTO, FMT_FASTA, FMT_FASTQ = 0, 1, 2
-CFG_NO_LUT, CFG_GENERIC, CFG_TIMING, CFG_EXACT_SCAN = 0x1, 0x2, 0x4, 0x8
+CFG_NO_LUT, CFG_GENERIC, CFG_TIMING, CFG_EXACT_SCAN, CFG_NO_FUSE = 0x1, 0x2, 0x4, 0x8, 0x10
 KEY_SHORT, KEY_NONCANON = 1 << 48, 1 << 49
 
 # every symbol include/sabreur_gpu.h declares

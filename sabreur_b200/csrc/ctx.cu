@@ -36,9 +36,11 @@ struct MatchLaunch {
     const uint8_t* text; uint32_t nbytes;
     uint16_t* assign; uint32_t* rec_off; uint64_t* key_out; uint32_t* cta_cnt; uint32_t nbins;
     int grid;
+    int fused; uint32_t nbits; uint32_t* bin_count; uint32_t* bin_start; uint32_t* order;
 };
 size_t match_smem(uint32_t n, uint32_t stride, uint32_t nbins, bool generic);
 cudaError_t match_prepare();
+int match_fused_max_grid(int device, int mode, size_t smem);
 cudaError_t match_build_lut(const uint2* d_tab, uint32_t n, uint32_t m, uint32_t k, uint16_t* d_lut, cudaStream_t stream);
 cudaError_t match_launch(const MatchLaunch& L, cudaStream_t stream);
 // k_partition.cu
@@ -126,6 +128,7 @@ struct sbr_ctx {
     uint16_t* d_lut = nullptr;
     uint64_t lut_entries = 0;
     PartitionPlan plan{};
+    bool fused = false;  // match + partition in one cooperative launch
     std::vector<Slot> slots;
     std::string err;
     // timing ring
@@ -239,6 +242,15 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
     CU(c, partition_prepare());
     c->plan = partition_plan(c->nbins, c->max_records, c->sms);
     if (match_smem(n, k, c->nbins, !c->packed) > 200 * 1024) return fail(c, SBR_E_UNSUPPORTED, "barcode table too large");
+    const bool will_lut = c->packed && !(cfg->flags & SBR_CFG_NO_LUT) && k <= 12;
+    if (!(cfg->flags & SBR_CFG_NO_FUSE)) {
+        // kernel 3 rides in the match kernel's launch when the whole grid can be resident at once
+        const int cap = match_fused_max_grid(cfg->device, !c->packed ? 2 : (will_lut ? 0 : 1), match_smem(n, k, c->nbins, !c->packed));
+        if (cap >= c->sms) {
+            c->fused = true;
+            if (c->plan.grid > cap) { c->plan.grid = cap; c->plan.V = (uint32_t)cap * 8u; }
+        }
+    }
 
     if (c->packed) {
         std::vector<uint2> tab(n);
@@ -374,13 +386,16 @@ static int launch_pipeline(sbr_ctx* c, Slot& s, const uint8_t* d_text, uint32_t 
         L.text = d_text; L.nbytes = nbytes;
         L.assign = s.d_assign; L.rec_off = s.d_rec_off; L.key_out = s.d_key; L.cta_cnt = s.d_cta_cnt; L.nbins = c->nbins;
         L.grid = c->plan.grid;
+        L.fused = c->fused ? 1 : 0; L.nbits = c->plan.nbits;
+        L.bin_count = s.d_bin_count; L.bin_start = s.d_bin_start; L.order = s.d_order;
         CU(c, match_launch(L, st));
     }
     if (ev) CU(c, cudaEventRecord(ev[2], st));
-    CU(c, partition_launch(s.d_assign, s.d_hdr, c->nbins, s.d_cta_cnt, s.d_bin_count, s.d_bin_start, s.d_order,
-                           s.d_done, c->plan, st));
+    if (!c->fused)
+        CU(c, partition_launch(s.d_assign, s.d_hdr, c->nbins, s.d_cta_cnt, s.d_bin_count, s.d_bin_start, s.d_order,
+                               s.d_done, c->plan, st));
     if (ev) CU(c, cudaEventRecord(ev[3], st));
-    c->launches += (fmt == SBR_FMT_FASTA ? 2 : 1) + 1 + 2;  // look-back scan (+finish), match, partition
+    c->launches += (fmt == SBR_FMT_FASTA ? 2 : 1) + 1 + (c->fused ? 0 : 2);  // look-back scan (+finish), match, partition
     return SBR_OK;
 }
 

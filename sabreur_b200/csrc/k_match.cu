@@ -12,7 +12,11 @@
 // first-match lookup table (built by the same XOR+popc routine over all 4^k keys) and the per-read
 // work becomes one L1/L2 gather; reads with invalid bases still take the table walk.
 // Generic path (non-ACGT barcode bytes or bc_len > 16): byte-exact compare on the raw text.
+#include <cooperative_groups.h>
+
 #include "scan_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace sbr {
 
@@ -68,20 +72,49 @@ __device__ __forceinline__ void slice_range(uint32_t n, uint32_t V, uint32_t v, 
     hi = b < n ? (uint32_t)b : n;
 }
 
+struct MatchArgs {
+    RecSource src;
+    const BatchHeader* hdr;
+    const uint2* g_tab; uint32_t n, m, code_mask;
+    const uint16_t* lut;
+    const uint8_t* text; uint32_t nbytes;
+    const uint8_t* g_rows; const uint32_t* g_lens; uint32_t stride, k;
+    uint16_t* assign; uint32_t* rec_off; uint64_t* key_out; uint32_t* cta_cnt; uint32_t nbins;
+    // FUSED only: kernel 3's outputs
+    uint32_t nbits; uint32_t* bin_count; uint32_t* bin_start; uint32_t* order;
+};
+
+// lanes holding the same bin as this lane, from one ballot per bit of the bin index (same as k_partition.cu)
+__device__ __forceinline__ uint32_t same_bin_lanes(uint32_t bin, uint32_t nbits, bool live) {
+    uint32_t peers = __ballot_sync(0xFFFFFFFFu, live);
+    if (!live) peers = ~peers;
+    for (uint32_t k = 0; k < nbits; ++k) {
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, (bin >> k) & 1u);
+        peers &= ((bin >> k) & 1u) ? b : ~b;
+    }
+    return peers;
+}
+
 // MODE 0: first-match LUT, 1: XOR+popc table walk, 2: byte-exact compare on the raw text.
 // Every warp owns a contiguous slice of the batch's records (the slices of kernel 3): it reads the
 // scan words (compacting the fast scan's per-region segments into the dense rec_off array on the way),
 // writes the assignments and counts its bins in shared memory -> cta_cnt[bin][cta].
-template <int MODE>
-__global__ void __launch_bounds__(MATCH_THREADS) k_match(RecSource src, const BatchHeader* __restrict__ hdr,
-                                                         const uint2* __restrict__ g_tab, uint32_t n, uint32_t m,
-                                                         uint32_t code_mask, const uint16_t* __restrict__ lut,
-                                                         const uint8_t* __restrict__ text, uint32_t nbytes,
-                                                         const uint8_t* __restrict__ g_rows,
-                                                         const uint32_t* __restrict__ g_lens, uint32_t stride, uint32_t k,
-                                                         uint16_t* __restrict__ assign, uint32_t* __restrict__ rec_off,
-                                                         uint64_t* __restrict__ key_out, uint32_t* __restrict__ cta_cnt,
-                                                         uint32_t nbins) {
+// FUSED (cooperative launch, every CTA resident): kernel 3 follows in the same launch -- grid barrier, the per-bin
+// scans over CTAs spread over the grid, grid barrier, cursors from the counts still sitting in shared memory, scatter.
+template <int MODE, bool FUSED>
+__global__ void __launch_bounds__(MATCH_THREADS) k_match(const MatchArgs A) {
+    const RecSource& src = A.src;
+    const BatchHeader* __restrict__ hdr = A.hdr;
+    const uint2* __restrict__ g_tab = A.g_tab;
+    const uint32_t n = A.n, m = A.m, code_mask = A.code_mask, nbytes = A.nbytes, stride = A.stride, k = A.k, nbins = A.nbins;
+    const uint16_t* __restrict__ lut = A.lut;
+    const uint8_t* __restrict__ text = A.text;
+    const uint8_t* __restrict__ g_rows = A.g_rows;
+    const uint32_t* __restrict__ g_lens = A.g_lens;
+    uint16_t* assign = A.assign;
+    uint32_t* __restrict__ rec_off = A.rec_off;
+    uint64_t* __restrict__ key_out = A.key_out;
+    uint32_t* cta_cnt = A.cta_cnt;
     extern __shared__ __align__(16) uint8_t s_mem[];
     // layout: [warps][nbins] histogram | region_base copy | table
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_mem);
@@ -213,6 +246,106 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(RecSource src, const Ba
         for (int w = 0; w < WARPS; ++w) run += s_hist[(size_t)w * nbins + b];
         cta_cnt[(size_t)b * gridDim.x + blockIdx.x] = run;
     }
+    if (!FUSED) return;
+
+    // ---- kernel 3 inside the same launch -----------------------------------------------------------------------
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t s_warp[WARPS];
+    const uint32_t G = gridDim.x;
+    __threadfence();
+    grid.sync();
+    // per bin: exclusive scan of the CTA totals in place (bins dealt round-robin to the CTAs), bin totals -> bin_count
+    for (uint32_t b = blockIdx.x; b < nbins; b += G) {
+        uint32_t* row = cta_cnt + (size_t)b * G;
+        constexpr int CH = 4;
+        uint32_t carry = 0;
+        for (uint32_t base = 0; base < G; base += MATCH_THREADS * CH) {
+            const uint32_t i0 = base + threadIdx.x * CH;
+            uint32_t x[CH], sum = 0;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                x[j] = i0 + j < G ? __ldcg(row + i0 + j) : 0u;
+                sum += x[j];
+            }
+            const uint32_t inc = warp_incl_scan(sum, lane);
+            if (lane == 31) s_warp[warp] = inc;
+            __syncthreads();
+            uint32_t pre = carry + inc - sum, tot = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const uint32_t t = s_warp[w];
+                if (w < warp) pre += t;
+                tot += t;
+            }
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                if (i0 + j < G) row[i0 + j] = pre;
+                pre += x[j];
+            }
+            carry += tot;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) A.bin_count[b] = carry;
+    }
+    __threadfence();
+    grid.sync();
+    // bin_start = exclusive scan of bin_count (every CTA for itself; CTA 0 publishes it), then the warps' cursors:
+    // bin_start + what earlier CTAs hold + what the CTA's earlier warps hold (their counts are still in s_hist)
+    {
+        uint32_t carry = 0;
+        for (uint32_t base = 0; base < nbins; base += MATCH_THREADS) {
+            const uint32_t b = base + threadIdx.x;
+            const uint32_t x = b < nbins ? __ldcg(A.bin_count + b) : 0u;
+            const uint32_t inc = warp_incl_scan(x, lane);
+            if (lane == 31) s_warp[warp] = inc;
+            __syncthreads();
+            uint32_t pre = carry + inc - x, tot = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const uint32_t t = s_warp[w];
+                if (w < warp) pre += t;
+                tot += t;
+            }
+            if (b < nbins) {
+                if (blockIdx.x == 0) A.bin_start[b] = pre;
+                uint32_t run = pre + __ldcg(cta_cnt + (size_t)b * G + blockIdx.x);
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) {
+                    const uint32_t t = s_hist[(size_t)w * nbins + b];
+                    s_hist[(size_t)w * nbins + b] = run;
+                    run += t;
+                }
+            }
+            carry += tot;
+            __syncthreads();
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) A.bin_start[nbins] = carry;
+    }
+    __syncthreads();
+    // stable scatter of the warp's own slice (its assignments come back from L2)
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t g0 = lo; g0 < hi; g0 += 32 * U) {
+        uint32_t bins[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t i = g0 + u * 32 + lane;
+            bins[u] = i < hi ? (uint32_t)assign[i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t i = g0 + u * 32 + lane;
+            if (g0 + u * 32 >= hi) break;  // warp-uniform
+            const bool live = i < hi;
+            const uint32_t bin = bins[u];
+            const uint32_t peers = same_bin_lanes(bin, A.nbits, live);
+            const uint32_t rank = __popc(peers & lt);
+            const uint32_t at = live ? mine[bin] : 0u;  // every lane of a group reads the group's cursor ...
+            __syncwarp();
+            if (live && rank == 0) mine[bin] = at + __popc(peers);  // ... then its first lane advances it
+            if (live) A.order[at + rank] = i;
+            __syncwarp();
+        }
+    }
 }
 
 }  // namespace
@@ -237,6 +370,8 @@ struct MatchLaunch {
     // outputs
     uint16_t* assign; uint32_t* rec_off; uint64_t* key_out; uint32_t* cta_cnt; uint32_t nbins;
     int grid;  // = the partition plan's grid: the histogram slices are kernel 3's slices
+    // fused with kernel 3 (cooperative launch) when `fused`
+    int fused; uint32_t nbits; uint32_t* bin_count; uint32_t* bin_start; uint32_t* order;
 };
 
 size_t match_smem(uint32_t n, uint32_t stride, uint32_t nbins, bool generic) {
@@ -244,28 +379,56 @@ size_t match_smem(uint32_t n, uint32_t stride, uint32_t nbins, bool generic) {
     return (size_t)(MATCH_THREADS / 32) * nbins * 4u + (MAX_REGIONS + 2) * 4u + tab + 16;
 }
 
+using MatchKernel = void (*)(const MatchArgs);
+static MatchKernel match_kernel(int mode, bool fused) {
+    switch (mode * 2 + (fused ? 1 : 0)) {
+        case 0: return k_match<0, false>;
+        case 1: return k_match<0, true>;
+        case 2: return k_match<1, false>;
+        case 3: return k_match<1, true>;
+        case 4: return k_match<2, false>;
+        default: return k_match<2, true>;
+    }
+}
+
 cudaError_t match_prepare() {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_match<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_match<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_match<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) != cudaSuccess) return e;
+    for (int mode = 0; mode < 3; ++mode)
+        for (int f = 0; f < 2; ++f)
+            if ((e = cudaFuncSetAttribute(match_kernel(mode, f != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) !=
+                cudaSuccess)
+                return e;
     return cudaFuncSetAttribute(k_build_lut, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
 }
 
+// the largest grid of the fused kernel that is resident all at once (a cooperative launch needs that); 0 = unsupported
+int match_fused_max_grid(int device, int mode, size_t smem) {
+    int coop = 0, sms = 0, per_sm = 0;
+    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess || !coop) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel(mode, true), MATCH_THREADS, smem) != cudaSuccess) return 0;
+    return per_sm * sms;
+}
+
 cudaError_t match_launch(const MatchLaunch& L, cudaStream_t stream) {
-    RecSource src{L.key_dense, L.seg_key, L.seg_rec_off, L.region_base, L.cap_r};
     const bool generic = L.tab == nullptr;
-    uint32_t code_mask = L.k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * L.k)) - 1u);
-    size_t smem = match_smem(L.n, L.stride, L.nbins, generic);
-    if (generic)
-        k_match<2><<<L.grid, MATCH_THREADS, smem, stream>>>(src, L.hdr, nullptr, L.n, L.m, 0u, nullptr, L.text, L.nbytes, L.rows,
-                                                            L.lens, L.stride, L.k, L.assign, L.rec_off, L.key_out, L.cta_cnt, L.nbins);
-    else if (L.lut)
-        k_match<0><<<L.grid, MATCH_THREADS, smem, stream>>>(src, L.hdr, L.tab, L.n, L.m, code_mask, L.lut, nullptr, 0u, nullptr,
-                                                            nullptr, 0u, L.k, L.assign, L.rec_off, L.key_out, L.cta_cnt, L.nbins);
-    else
-        k_match<1><<<L.grid, MATCH_THREADS, smem, stream>>>(src, L.hdr, L.tab, L.n, L.m, code_mask, nullptr, nullptr, 0u, nullptr,
-                                                            nullptr, 0u, L.k, L.assign, L.rec_off, L.key_out, L.cta_cnt, L.nbins);
+    const int mode = generic ? 2 : (L.lut ? 0 : 1);
+    MatchArgs A{};
+    A.src = RecSource{L.key_dense, L.seg_key, L.seg_rec_off, L.region_base, L.cap_r};
+    A.hdr = L.hdr;
+    A.g_tab = L.tab; A.n = L.n; A.m = L.m;
+    A.code_mask = generic ? 0u : (L.k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * L.k)) - 1u));
+    A.lut = L.lut;
+    A.text = generic ? L.text : nullptr; A.nbytes = generic ? L.nbytes : 0u;
+    A.g_rows = L.rows; A.g_lens = L.lens; A.stride = generic ? L.stride : 0u; A.k = L.k;
+    A.assign = L.assign; A.rec_off = L.rec_off; A.key_out = L.key_out; A.cta_cnt = L.cta_cnt; A.nbins = L.nbins;
+    A.nbits = L.nbits; A.bin_count = L.bin_count; A.bin_start = L.bin_start; A.order = L.order;
+    const size_t smem = match_smem(L.n, L.stride, L.nbins, generic);
+    if (L.fused) {
+        void* args[] = {&A};
+        return cudaLaunchCooperativeKernel((const void*)match_kernel(mode, true), dim3(L.grid), dim3(MATCH_THREADS), args, smem, stream);
+    }
+    match_kernel(mode, false)<<<L.grid, MATCH_THREADS, smem, stream>>>(A);
     return cudaGetLastError();
 }
 

@@ -32,9 +32,11 @@ def _check_against_oracle(gpu, text: bytes, barcodes, m, **kw):
     dm = gpu["demux"]
     exp = orc.demux(text, barcodes, m)
     user_flags = kw.pop("flags", 0)
-    # both record scans: the region-parallel one (default) and the look-back one (forced)
-    for scan_flag in (gpu["ffi"].CFG_EXACT_SCAN, 0):
-        got = dm.demux_bytes(text, barcodes, m, flags=user_flags | scan_flag, **kw)
+    # both record scans: the region-parallel one (default) and the look-back one (forced); match + partition as one
+    # cooperative launch (default) and as separate launches
+    ffi = gpu["ffi"]
+    for scan_flag, extra in ((ffi.CFG_EXACT_SCAN, 0), (0, 0), (0, ffi.CFG_NO_FUSE)):
+        got = dm.demux_bytes(text, barcodes, m, flags=user_flags | scan_flag | extra, **kw)
         assert got["bad"] is None and not (got["status"] & gpu["ffi"].ST_ERROR_MASK)
         assert got["assign"].tolist() == exp["assign"].tolist()
         assert got["bin_count"].tolist() == exp["bin_count"].tolist()

@@ -162,6 +162,10 @@ struct Sink {  // where the records of one bin go in this pass
     uint64_t written_records = 0, batch_records = 0;
 };
 
+struct Gpu;
+std::vector<Gpu> take_pooled(const std::vector<uint8_t>& key);
+void give_pooled(const std::vector<uint8_t>& key, const std::vector<Gpu>& gpus);
+
 class Pass {
 public:
     Pass(const std::string& path, std::vector<FILE*> bin_files, const std::vector<std::string>& barcodes, uint8_t mismatch,
@@ -185,7 +189,15 @@ public:
         cap_ = opt.batch_bytes;
         reserve_ = std::min<uint64_t>(cap_ / 8, 16ull << 20);
         gpus_.resize(G_);
+        // contexts (pinned slots, device workspaces, the match table) are kept for the next pass with the same
+        // table and geometry: the reverse pass of a paired-end run reuses the forward pass's
+        pool_key_.assign(tab.begin(), tab.end());
+        for (uint32_t v : {k, (uint32_t)mismatch, S_, (uint32_t)(cap_ >> 20), (uint32_t)G_})
+            for (int j = 0; j < 4; ++j) pool_key_.push_back((uint8_t)(v >> (8 * j)));
+        for (uint32_t l : lens) pool_key_.push_back((uint8_t)l);
+        std::vector<Gpu> pooled = take_pooled(pool_key_);
         for (int g = 0; g < G_; ++g) {
+            if ((size_t)g < pooled.size()) { gpus_[g] = pooled[g]; continue; }
             sbr_config cfg{};
             cfg.device = g; cfg.fmt = SBR_FMT_AUTO; cfg.n_barcodes = (uint32_t)barcodes.size(); cfg.bc_len = k;
             cfg.barcodes = tab.data(); cfg.bc_lens = lens.data(); cfg.mismatch = mismatch; cfg.n_slots = S_;
@@ -201,7 +213,8 @@ public:
         }
     }
     ~Pass() {
-        for (auto& g : gpus_) sbr_destroy(g.ctx);
+        if (!error_ && !gpus_.empty() && gpus_.back().ctx) { give_pooled(pool_key_, gpus_); return; }
+        for (auto& g : gpus_) sbr_destroy(g.ctx);  // after a failure nothing is assumed about the contexts' state
     }
 
     // strict: SE semantics (`record?`, demux.rs:50: a bad record is an error); otherwise PE semantics (the loop
@@ -510,6 +523,7 @@ private:
         }
     }
 
+    std::vector<uint8_t> pool_key_;
     std::string path_;
     HostOptions opt_;
     Format out_format_;
@@ -536,6 +550,27 @@ private:
     uint32_t bad_flags_ = 0;
     uint64_t bad_record_ = 0, records_before_ = 0;
 };
+
+// one parked set of contexts (a process runs one table at a time)
+std::mutex g_pool_m;
+std::vector<uint8_t> g_pool_key;
+std::vector<Gpu> g_pool;
+std::vector<Gpu> take_pooled(const std::vector<uint8_t>& key) {
+    std::lock_guard<std::mutex> l(g_pool_m);
+    std::vector<Gpu> out;
+    if (!g_pool.empty() && g_pool_key == key) out.swap(g_pool);
+    else {
+        for (auto& g : g_pool) sbr_destroy(g.ctx);
+        g_pool.clear();
+    }
+    return out;
+}
+void give_pooled(const std::vector<uint8_t>& key, const std::vector<Gpu>& gpus) {
+    std::lock_guard<std::mutex> l(g_pool_m);
+    for (auto& g : g_pool) sbr_destroy(g.ctx);
+    g_pool = gpus;
+    g_pool_key = key;
+}
 
 std::vector<std::string> barcode_list(const Barcode& bd) {
     if (bd.rows.empty()) throw std::runtime_error("Barcode data is empty");  // demux.rs:31-33

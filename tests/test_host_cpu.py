@@ -104,3 +104,20 @@ def test_cli_fails_loudly_without_a_gpu(tmp_path):
         pytest.skip("a GPU is present")
     r = _run([_fx("bc_se.txt"), _fx("test.fq"), "-o", "out"], tmp_path)
     assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+def test_cli_barcode_file_errors(tmp_path):
+    """utils.rs:103-112 (no tab -> error, exit 1) and main.rs:148 (a row without enough columns panics, exit 101);
+    both happen before any GPU work"""
+    bad = tmp_path / "notab.txt"
+    bad.write_text("ACGT bc1.fq\n")
+    r = _run([str(bad), _fx("test.fq"), "-o", "o1"], tmp_path)
+    assert r.returncode == 1 and "Input string is not tab-delimited" in r.stderr
+    blank = tmp_path / "blank.txt"
+    blank.write_text("ACGT\tbc1.fq\n\nCCGT\tbc2.fq\n")
+    r = _run([str(blank), _fx("test.fq"), "-o", "o2"], tmp_path)
+    assert r.returncode == 101 and "panicked" in r.stderr
+    two = tmp_path / "two.txt"
+    two.write_text("ACGT\tbc1_R1.fq\n")
+    r = _run([str(two), _fx("test.fq"), _fx("test.fq"), "-o", "o3"], tmp_path)  # paired-end needs three columns
+    assert r.returncode == 101

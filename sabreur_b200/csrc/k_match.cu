@@ -143,8 +143,11 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(const MatchArgs A) {
     uint32_t* mine = s_hist + (size_t)warp * nbins;
     uint32_t lo, hi;
     slice_range(nrec, V, v, lo, hi);
-    // four records per lane and step: all loads of a step are issued before the first use
-    constexpr int U = 4;
+    // U records per lane and step: all loads of a step are issued before the first use
+#ifndef SBR_MATCH_U
+#define SBR_MATCH_U 4
+#endif
+    constexpr int U = SBR_MATCH_U;
     uint32_t reg_lo = 1, reg_hi = 0;  // record range [reg_lo, reg_hi) of the region found last, and where its segment starts
     size_t reg_at = 0;
     for (uint32_t g0 = lo; g0 < hi; g0 += 32 * U) {

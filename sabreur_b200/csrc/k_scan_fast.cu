@@ -37,16 +37,26 @@ namespace {
 constexpr uint32_t UNKNOWN_L = 0xFFFFFFFFu;
 constexpr int FAST_WARPS = SCAN_THREADS / 32;
 // A lane masks 48 bytes in each of FAST_UNITS units of its warp's slice; one warp scan serves all of them.
-constexpr int FAST_UNITS = 2;
+// Two geometries (SBR_SCAN_SINGLE selects at compile time):
+//   double-buffered: 2 units per lane, 3 KB slices, 24 KB tiles, two stages (the next tile loads while this one is scanned)
+//   single-buffered: 3 units per lane, 4.5 KB slices, 36 KB tiles, one stage (the per-slice bookkeeping is amortised over
+//                    half as much again and a slice ends ~14 records, which fills the record lanes; the other
+//                    resident CTAs cover a CTA's load)
+#ifndef SBR_SCAN_SINGLE
+#define SBR_SCAN_SINGLE 1
+#endif
+constexpr int FAST_UNITS = SBR_SCAN_SINGLE ? 3 : 2;
 constexpr int UNIT_BYTES = 32 * SCAN_BYTES_PER_THREAD;  // 1536 B: one 48-byte chunk per lane
-constexpr int WARP_SLICE = FAST_UNITS * UNIT_BYTES;     // 3072 B
-constexpr int FAST_TILE = FAST_WARPS * WARP_SLICE;      // 24 KB
-constexpr int FAST_STAGES = 2;
+constexpr int WARP_SLICE = FAST_UNITS * UNIT_BYTES;     // 3072 / 4608 B
+constexpr int FAST_TILE = FAST_WARPS * WARP_SLICE;      // 24 / 36 KB
+constexpr int FAST_STAGES = SBR_SCAN_SINGLE ? 1 : 2;
 // every stage is preceded by a copy of the last TAIL_PAD bytes of the previous tile, so that a record which began there is
 // still addressable in shared memory at (stage base + position - tile start)
 constexpr int TAIL_PAD = 512;
 __host__ __device__ constexpr int stage_stride(int fmt) { return (fmt == SBR_FMT_FASTQ ? TAIL_PAD : 0) + FAST_TILE; }  // FASTA has no use for the pad
-constexpr int WL_CAP = 188;
+constexpr int WL_CAP = SBR_SCAN_SINGLE ? 284 : 188;  // newline positions per warp slice held in shared memory (>= 16.3-byte lines on average)
+constexpr int CNT_BITS = FAST_UNITS == 2 ? 16 : 10;   // per-unit newline counts of a slice share one word (valid while the slice fits WL_CAP)
+constexpr uint32_t CNT_MASK = (1u << CNT_BITS) - 1u;
 constexpr int FASTA_CHUNKS = (WL_CAP + 31) / 32;
 constexpr uint32_t FASTA_START = 1u << 30;  // list entry flag: a FASTA record starts behind this newline
 constexpr uint32_t POS_MASK = FASTA_START - 1u;  // newline positions per warp slice held in shared memory (>= 16.4-byte lines on average)
@@ -250,7 +260,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
         for (int s = 0; s < FAST_STAGES; ++s)
             if (t_lo + s < t_hi) issue(s, t_lo + s);
 
-    // Tile loop, ONE block barrier per 24 KB tile.  Before it every warp has compacted the newlines of its own
+    // Tile loop, ONE block barrier per tile while it is scanned (a second one at its end when single-buffered).  Before it every warp has compacted the newlines of its own
     // slice and published their number and its last four positions; after it every warp knows its place in the
     // line cycle, fetches the four newlines before its slice and evaluates the records ending in the slice.
     // The barrier of tile t+1 doubles as "everybody is done with tile t", after which thread 0 refills tile
@@ -262,7 +272,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
         const bool overrun = tile >= t_hi;
         if (overrun) {
             if (FMT == SBR_FMT_FASTA) break;
-            __syncthreads();  // records of the previous tile are complete: S.done / S.synced are final
+            if (FAST_STAGES > 1) __syncthreads();  // records of the previous tile are complete: S.done / S.synced are final
             if (S.done || !S.synced || S.fail) break;
         }
         const int s = it % FAST_STAGES;
@@ -277,7 +287,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
         // ---- newline masks of this lane's 48 bytes in each unit of the warp's slice ---------------------
         const uint32_t woff = (uint32_t)warp * WARP_SLICE + (uint32_t)lane * SCAN_BYTES_PER_THREAD;
         uint32_t m_lo[FAST_UNITS], m_hi[FAST_UNITS];
-        uint32_t cn2 = 0;  // per-unit counts, 16 bits each
+        uint32_t cn2 = 0, c_all = 0;  // per-unit counts, CNT_BITS each; their sum
 #pragma unroll
         for (int j = 0; j < FAST_UNITS; ++j) {
             const uint32_t uoff = woff + j * UNIT_BYTES;
@@ -289,12 +299,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
                 m_lo[j] &= nv >= 32 ? 0xFFFFFFFFu : ((1u << nv) - 1u);
                 m_hi[j] &= nv > 32 ? ((1u << (nv - 32)) - 1u) : 0u;
             }
-            cn2 |= (uint32_t)(__popc(m_lo[j]) + __popc(m_hi[j])) << (16 * j);
+            const uint32_t cj = (uint32_t)(__popc(m_lo[j]) + __popc(m_hi[j]));
+            cn2 |= cj << (CNT_BITS * j);
+            c_all += cj;
         }
+        const uint32_t n_w = __reduce_add_sync(0xFFFFFFFFu, c_all);  // newlines of the whole slice (exact even if fields overflow)
         const uint32_t incl_n = warp_incl_scan(cn2, lane);
         const uint32_t tot_n = __shfl_sync(0xFFFFFFFFu, incl_n, 31);
         const uint32_t ex_n = incl_n - cn2;
-        const uint32_t n0 = tot_n & 0xFFFFu, n_w = n0 + (tot_n >> 16);  // newlines of unit 0 / of the whole slice
         uint32_t nr_w = 0;  // FASTA: record starts of the slice
         // read before the barrier: thread 0 may flip it right after that barrier, and every thread has to take
         // the same decision about the extra barrier below
@@ -309,8 +321,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
             bool crlf = false;
             const uint32_t sm_a = smem_u32(sm);
 #pragma unroll
+            uint32_t unit_base = 0;  // newlines in the slice's earlier units
+#pragma unroll
             for (int j = 0; j < FAST_UNITS; ++j) {
-                const uint32_t idx = j ? n0 + (ex_n >> 16) : (ex_n & 0xFFFFu);
+                const uint32_t idx = unit_base + ((ex_n >> (CNT_BITS * j)) & CNT_MASK);
+                unit_base += (tot_n >> (CNT_BITS * j)) & CNT_MASK;
                 uint32_t a = wl_addr + 4u * idx;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -357,11 +372,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
             if (FMT == SBR_FMT_FASTA && lane < 2) S.whead[par][warp][lane] = nn > (uint32_t)lane ? (wl[GHOSTS + lane] & POS_MASK) : NOPOS;
         }
         __syncthreads();  // the tile's barrier
-        if (tid == 0 && it >= 1 && !overrun) {  // tile it-1 is finished by everybody: refill its stage
+        if (FAST_STAGES > 1 && tid == 0 && it >= 1 && !overrun) {  // tile it-1 is finished by everybody: refill its stage
             const uint32_t nt = tile - 1 + FAST_STAGES;
             if (nt < t_hi) issue((it - 1) % FAST_STAGES, nt);
         }
-        if (FMT == SBR_FMT_FASTQ && warp == FAST_WARPS - 2) {  // the tile's last TAIL_PAD bytes -> the pad in front of the other stage (the next tile)
+        if (FAST_STAGES > 1 && FMT == SBR_FMT_FASTQ && warp == FAST_WARPS - 2) {  // the tile's last TAIL_PAD bytes -> the pad in front of the other stage (the next tile)
             const uint4 v = *reinterpret_cast<const uint4*>(sm + FAST_TILE - TAIL_PAD + 16 * lane);
             *reinterpret_cast<uint4*>(stage_buf + (s ^ 1) * STAGE_STRIDE - TAIL_PAD + 16 * lane) = v;
         }
@@ -582,6 +597,18 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
                 if (why == 1 || (why == 2 && A.final_batch)) S.fail = 1;
                 A.seg_rec_off[0] = 0;
                 A.seg_key[0] = key;
+            }
+        }
+        if (FAST_STAGES == 1) {
+            __syncthreads();  // everybody is done with the tile's text (and S.done / S.synced are final)
+            if (warp == 0) {
+                if (FMT == SBR_FMT_FASTQ) {  // the tile's last TAIL_PAD bytes -> the pad in front of the stage
+                    const uint4 v = *reinterpret_cast<const uint4*>(sm + FAST_TILE - TAIL_PAD + 16 * lane);
+                    __syncwarp();
+                    *reinterpret_cast<uint4*>(stage_buf - TAIL_PAD + 16 * lane) = v;
+                    __syncwarp();
+                }
+                if (lane == 0 && tile + 1 < t_hi) issue(0, tile + 1);
             }
         }
     }

@@ -230,6 +230,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
         uint32_t bytes = (valid + 15u) & ~15u;  // the text buffer is padded to 16 bytes
         mbar_expect_tx(&S.full_bar[s], bytes);
         bulk_g2s_hint(stage_buf + s * STAGE_STRIDE, A.text + lo, bytes, &S.full_bar[s], text_policy);
+        if (FAST_STAGES == 1 && tile + 1 < A.ntiles) {
+            // single-buffered: the load of the NEXT tile can only start when this one has been scanned, so at least
+            // bring it into L2 now (the region's last tile prefetches the one a FASTQ region runs over into)
+            const uint32_t nlo = lo + (uint32_t)FAST_TILE;
+            bulk_prefetch_l2(A.text + nlo, (min((uint32_t)FAST_TILE, A.nbytes - nlo) + 15u) & ~15u);
+        }
     };
 
     if (tid == 0) {

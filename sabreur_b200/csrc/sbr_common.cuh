@@ -125,6 +125,11 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32
         : "memory");
 }
 
+// bulk prefetch global -> L2 (no shared memory involved): the tile after next is on its way while this one is scanned
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // single-copy-atomic 128-bit accesses for the look-back descriptors (SASS LDG/STG.E.128.STRONG.GPU)
 __device__ __forceinline__ uint4 ld_desc(const uint4* p) {
     uint4 v;

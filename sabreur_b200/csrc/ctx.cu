@@ -31,7 +31,7 @@ struct MatchLaunch {
     const uint64_t* key_dense; const uint64_t* seg_key; const uint32_t* seg_rec_off; const uint32_t* region_base;
     uint32_t cap_r;
     const BatchHeader* hdr;
-    const uint2* tab; const uint16_t* lut; const uint8_t* rows; const uint32_t* lens;
+    const uint2* tab; const uint16_t* lut; const uint16_t* lut1; uint32_t uniform; const uint8_t* rows; const uint32_t* lens;
     uint32_t n, m, k, stride;
     const uint8_t* text; uint32_t nbytes;
     uint16_t* assign; uint32_t* rec_off; uint64_t* key_out; uint32_t* cta_cnt; uint32_t nbins;
@@ -126,6 +126,8 @@ struct sbr_ctx {
     uint8_t* d_rows = nullptr;     // raw rows (generic path)
     uint32_t* d_lens = nullptr;
     uint16_t* d_lut = nullptr;
+    uint16_t* d_lut1 = nullptr;  // first-match table for mismatch - 1 (reads with one non-ACGT base)
+    bool uniform = false;        // every row spans the whole match window
     uint64_t lut_entries = 0;
     PartitionPlan plan{};
     bool fused = false;  // match + partition in one cooperative launch
@@ -188,7 +190,7 @@ extern "C" void sbr_destroy(sbr_ctx* c) {
     cudaSetDevice(c->device);
     for (auto& s : c->slots) free_slot(s);
     for (auto e : c->ev) cudaEventDestroy(e);
-    cudaFree(c->d_tab); cudaFree(c->d_rows); cudaFree(c->d_lens); cudaFree(c->d_lut);
+    cudaFree(c->d_tab); cudaFree(c->d_rows); cudaFree(c->d_lens); cudaFree(c->d_lut); cudaFree(c->d_lut1);
     delete c;
 }
 
@@ -231,6 +233,8 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
         for (uint32_t j = 0; j < len; ++j) acgt &= is_acgt(c->rows[(size_t)b * k + j]);
     }
     c->packed = acgt && k <= 16 && !(cfg->flags & SBR_CFG_GENERIC);
+    c->uniform = true;
+    for (uint32_t b = 0; b < n; ++b) c->uniform = c->uniform && c->lens[b] == k;
     c->max_records = cfg->max_records ? cfg->max_records : (uint32_t)(cfg->batch_bytes / 32 + 16);
     c->max_tiles = scan_tiles((uint32_t)cfg->batch_bytes) + 1;
     c->timing = (cfg->flags & SBR_CFG_TIMING) != 0;
@@ -268,6 +272,10 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
             c->lut_entries = 1ull << (2 * k);
             CU(c, cudaMalloc(&c->d_lut, c->lut_entries * sizeof(uint16_t)));
             CU(c, match_build_lut(c->d_tab, n, cfg->mismatch, k, c->d_lut, 0));
+            if (c->uniform && cfg->mismatch >= 1) {
+                CU(c, cudaMalloc(&c->d_lut1, c->lut_entries * sizeof(uint16_t)));
+                CU(c, match_build_lut(c->d_tab, n, cfg->mismatch - 1, k, c->d_lut1, 0));
+            }
             CU(c, cudaDeviceSynchronize());
         }
     } else {
@@ -381,7 +389,7 @@ static int launch_pipeline(sbr_ctx* c, Slot& s, const uint8_t* d_text, uint32_t 
         L.key_dense = s.d_key; L.seg_key = s.d_seg_key; L.seg_rec_off = s.d_seg_rec_off; L.region_base = s.d_region_base;
         L.cap_r = cap_r;
         L.hdr = s.d_hdr;
-        L.tab = c->packed ? c->d_tab : nullptr; L.lut = c->d_lut; L.rows = c->d_rows; L.lens = c->d_lens;
+        L.tab = c->packed ? c->d_tab : nullptr; L.lut = c->d_lut; L.lut1 = c->d_lut1; L.uniform = c->uniform ? 1u : 0u; L.rows = c->d_rows; L.lens = c->d_lens;
         L.n = c->cfg.n_barcodes; L.m = c->cfg.mismatch; L.k = c->cfg.bc_len; L.stride = c->cfg.bc_len;
         L.text = d_text; L.nbytes = nbytes;
         L.assign = s.d_assign; L.rec_off = s.d_rec_off; L.key_out = s.d_key; L.cta_cnt = s.d_cta_cnt; L.nbins = c->nbins;

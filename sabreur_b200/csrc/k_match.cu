@@ -77,6 +77,8 @@ struct MatchArgs {
     const BatchHeader* hdr;
     const uint2* g_tab; uint32_t n, m, code_mask;
     const uint16_t* lut;
+    const uint16_t* lut1;  // the same table for mismatch - 1 (NULL when m == 0 or the rows differ in length)
+    uint32_t uniform;      // every row is compared over the whole window
     const uint8_t* text; uint32_t nbytes;
     const uint8_t* g_rows; const uint32_t* g_lens; uint32_t stride, k;
     uint16_t* assign; uint32_t* rec_off; uint64_t* key_out; uint32_t* cta_cnt; uint32_t nbins;
@@ -207,9 +209,29 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(const MatchArgs A) {
                     if (usable) hit = first_match(s_tab, n, m, codes, spread16(inval));
                 } else {
                     if (usable && inval == 0) hit = __ldg(lut + codes);
-                    // reads with a non-ACGT base in the window (rare) cannot use the LUT: the warp walks the
-                    // table together, 32 rows per step, one such read at a time
-                    uint32_t todo = __ballot_sync(0xFFFFFFFFu, usable && inval != 0);
+                    // Reads with a non-ACGT base in the window: such a base differs from every barcode base
+                    // (src/utils.rs:120 compares bytes).  When all rows are compared over the whole window:
+                    //   * more invalid bases than the mismatch budget -> nothing can match;
+                    //   * exactly one, at position p -> a row matches iff it is within m-1 of the read on the other
+                    //     positions, i.e. iff it is within m-1 of the read with SOME base X put at p (X = the row's
+                    //     own base there).  The first such row is the smallest answer of the (m-1)-table over the
+                    //     four substitutions.
+                    // Everything else (rare) walks the table: the warp together, 32 rows per step, one read at a time.
+                    bool pending = usable && inval != 0;
+                    if (pending && A.uniform) {
+                        const uint32_t ninv = __popc(inval);
+                        if (ninv > m) pending = false;  // stays unknown
+                        else if (ninv == 1 && A.lut1) {
+                            const uint32_t sh = 2u * (uint32_t)(__ffs(inval) - 1);
+                            const uint32_t base = codes & ~(3u << sh);
+                            uint32_t r = n;
+#pragma unroll
+                            for (uint32_t X = 0; X < 4; ++X) r = min(r, (uint32_t)__ldg(A.lut1 + (base | (X << sh))));
+                            hit = r;
+                            pending = false;
+                        }
+                    }
+                    uint32_t todo = __ballot_sync(0xFFFFFFFFu, pending);
                     while (todo) {
                         const int srcl = __ffs(todo) - 1;
                         todo &= todo - 1;
@@ -367,7 +389,7 @@ struct MatchLaunch {
     uint32_t cap_r;
     const BatchHeader* hdr;
     // table
-    const uint2* tab; const uint16_t* lut; const uint8_t* rows; const uint32_t* lens;
+    const uint2* tab; const uint16_t* lut; const uint16_t* lut1; uint32_t uniform; const uint8_t* rows; const uint32_t* lens;
     uint32_t n, m, k, stride;
     const uint8_t* text; uint32_t nbytes;
     // outputs
@@ -421,7 +443,7 @@ cudaError_t match_launch(const MatchLaunch& L, cudaStream_t stream) {
     A.hdr = L.hdr;
     A.g_tab = L.tab; A.n = L.n; A.m = L.m;
     A.code_mask = generic ? 0u : (L.k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * L.k)) - 1u));
-    A.lut = L.lut;
+    A.lut = L.lut; A.lut1 = L.lut1; A.uniform = L.uniform;
     A.text = generic ? L.text : nullptr; A.nbytes = generic ? L.nbytes : 0u;
     A.g_rows = L.rows; A.g_lens = L.lens; A.stride = generic ? L.stride : 0u; A.k = L.k;
     A.assign = L.assign; A.rec_off = L.rec_off; A.key_out = L.key_out; A.cta_cnt = L.cta_cnt; A.nbins = L.nbins;

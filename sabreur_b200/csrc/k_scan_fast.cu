@@ -320,13 +320,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
         const bool fits = n_w <= (uint32_t)WL_CAP;  // warp-uniform
 
         // ---- compact the slice's newline positions (ascending) into the warp's list ---------------------
-        // FASTA entries also carry FASTA_START (bit 30: positions are below 2^30) when the next byte is '>', i.e. when
-        // a record starts right after the newline
         uint32_t start_bal[FASTA_CHUNKS] = {};  // FASTA: per 32 list entries, which ones are record starts
         if (fits) {
-            bool crlf = false;
-            const uint32_t sm_a = smem_u32(sm);
-#pragma unroll
             uint32_t unit_base = 0;  // newlines in the slice's earlier units
 #pragma unroll
             for (int j = 0; j < FAST_UNITS; ++j) {
@@ -336,35 +331,41 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t mm = half ? m_hi[j] : m_lo[j];
-                    const uint32_t o0 = woff + j * UNIT_BYTES + 32 * half;
-                    const uint32_t pos0 = lo + o0;
+                    const uint32_t pos0 = lo + woff + j * UNIT_BYTES + 32 * half;
                     while (mm) {
                         const uint32_t b = __ffs(mm) - 1;
                         mm &= mm - 1;
-                        uint32_t entry = pos0 + b;
-                        if (FMT == SBR_FMT_FASTA) {
-                            const uint32_t o = o0 + b;
-                            uint32_t nxt = 0;  // the byte behind the newline
-                            if (o + 1 < valid) nxt = lds_u8(sm_a + o + 1);
-                            else if (lo + o + 1 < A.nbytes) nxt = A.text[lo + o + 1];
-                            if (nxt == '>') entry |= FASTA_START;
-                            // CR before LF makes a FASTA batch non-canonical
-                            crlf |= o > 0 ? lds_u8(sm_a + o - 1) == '\r' : (lo > 0 && A.text[lo - 1] == '\r');
-                        }
-                        sts_u32(a, entry);
+                        sts_u32(a, pos0 + b);
                         a += 4u;
                     }
                 }
             }
             if (FMT == SBR_FMT_FASTA) {
-                if (crlf) S.crlf = 1;
+                // one lane per list entry: the byte behind the newline ('>' = a record starts there: the entry gets
+                // FASTA_START, bit 30 -- positions are below 2^30) and the byte before it (CR makes the batch non-canonical)
                 __syncwarp();
+                const uint32_t sm_a = smem_u32(sm);
+                bool crlf = false;
 #pragma unroll
                 for (int ch = 0; ch < FASTA_CHUNKS; ++ch) {
+                    if (ch * 32 >= (int)n_w) break;  // warp-uniform
                     const uint32_t jx = ch * 32 + lane;
-                    start_bal[ch] = __ballot_sync(0xFFFFFFFFu, jx < n_w && (wl[GHOSTS + jx] & FASTA_START));
+                    bool st = false;
+                    if (jx < n_w) {
+                        const uint32_t pos = wl[GHOSTS + jx], o = pos - lo;
+                        uint32_t nxt = 0, prv = 0;
+                        if (o + 1 < valid) nxt = lds_u8(sm_a + o + 1);
+                        else if (pos + 1 < A.nbytes) nxt = A.text[pos + 1];
+                        if (o > 0) prv = lds_u8(sm_a + o - 1);
+                        else if (pos > 0) prv = A.text[pos - 1];
+                        crlf |= prv == '\r';
+                        st = nxt == '>';
+                        if (st) wl[GHOSTS + jx] = pos | FASTA_START;
+                    }
+                    start_bal[ch] = __ballot_sync(0xFFFFFFFFu, st);
                     nr_w += __popc(start_bal[ch]);
                 }
+                if (crlf) S.crlf = 1;
             }
         } else if (lane == 0) {
             S.fail = 1;  // newline-dense slice: the exact scan's job

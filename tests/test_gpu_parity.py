@@ -307,3 +307,30 @@ def test_large_batch_properties(gpu):
     k = 50_000
     text = dev[: k * w.rec_bytes].cpu().numpy()
     assert np.array_equal(b.assign[:k], orc.demux(text, bcs, w.mismatch)["assign"])
+
+
+# ---- reads with non-ACGT bases in the match window: the (m-1)-table shortcut and the table walk -----------------
+@pytest.mark.parametrize("k,n_bc,m", [(6, 40, 1), (6, 40, 2), (8, 96, 1), (5, 30, 0), (10, 200, 2)])
+def test_reads_with_invalid_bases_in_the_window(gpu, k, n_bc, m):
+    rng = random.Random(k * 100 + n_bc + m)
+    bcs = []
+    while len(bcs) < n_bc:  # an adversarial table: near neighbours on purpose, no distance constraint
+        if bcs and rng.random() < 0.5:
+            b = bytearray(rng.choice(bcs))
+            b[rng.randrange(k)] = rng.choice(b"ACGT")
+            b = bytes(b)
+        else:
+            b = bytes(rng.choice(b"ACGT") for _ in range(k))
+        if b not in bcs:
+            bcs.append(b)
+    out = bytearray()
+    for i in range(6000):
+        pre = bytearray(rng.choice(bcs))
+        for _ in range(rng.choice((0, 0, 1, 1, 2, 3))):          # substitutions
+            pre[rng.randrange(k)] = rng.choice(b"ACGT")
+        for _ in range(rng.choice((0, 1, 1, 1, 2, 3))):          # invalid bases: N, lower case, IUPAC
+            pre[rng.randrange(k)] = rng.choice(b"NnacgtRY")
+        s = bytes(pre) + bytes(rng.choice(b"ACGT") for _ in range(rng.randint(0, 30)))
+        out += b"@r%d\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n"
+    for flags in (0, gpu["ffi"].CFG_NO_LUT):
+        _check_against_oracle(gpu, bytes(out), bcs, m, batch_bytes=1 << 20, flags=flags)

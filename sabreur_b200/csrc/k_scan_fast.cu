@@ -554,14 +554,17 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
             const ByteSrc B{sm, A.text, lo, lo + valid};
             const uint32_t rbase = S.rcnt[par] + pre_r + ((c == 0) ? 1u : 0u);  // records before this slice (record 0 of the batch counted)
             const uint32_t sbase = smem_u32(sm) - lo;  // shared-window address of batch position 0 (wraps)
-            uint32_t u0 = 0;  // starts in earlier chunks of the slice
+            // lane u takes the u-th flagged entry (every other newline of single-line FASTA is a start: going chunk by
+            // chunk would leave half of the lanes idle in twice as many passes)
+            for (uint32_t u = (uint32_t)lane; fits && u < nr_w; u += 32u) {
+                uint32_t idx = 0, rem = u;
 #pragma unroll
-            for (int ch = 0; ch < FASTA_CHUNKS; ++ch) {
-                if (!fits || ch * 32 >= (int)n_w) break;  // warp-uniform
-                const uint32_t bal = start_bal[ch];
-                if ((bal >> lane) & 1u) {
-                    const uint32_t idx = ch * 32 + lane;
-                    const uint32_t u = u0 + __popc(bal & ((1u << lane) - 1u));
+                for (int ch = 0; ch < FASTA_CHUNKS; ++ch) {
+                    const uint32_t cch = __popc(start_bal[ch]);
+                    if (rem < cch) { idx = ch * 32 + __fns(start_bal[ch], 0u, (int)rem + 1); break; }
+                    rem -= cch;
+                }
+                {
                     const uint32_t p = wl[GHOSTS + idx] & POS_MASK;
                     // the two newlines behind the record start (the header's, the first sequence line's): from the own
                     // list, or from the head the next slice published
@@ -595,7 +598,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
                     if (u == nr_w - 1)  // ascending over the tiles: a plain store per warp, the maximum is taken at the end
                         S.wlast[warp] = ((unsigned long long)(base + pre_n + idx + 1) << 32) | (unsigned long long)(p + 1);
                 }
-                u0 += __popc(bal);
             }
             if (tid == 0 && c == 0 && it == 0) {
                 uint64_t key;

@@ -583,8 +583,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
                         // known to lie on the first sequence line: the next newline is listed and far enough
                         if ((key >> 32) == 0) why = 0;
                         else {
+                            // (+1: the line may end in CR LF, and the CR must stay outside the window too)
                             const uint32_t e2 = ahead(idx + 2);
-                            if (e2 != NOPOS && e2 > hend + A.bc_len) why = 0;
+                            if (e2 != NOPOS && e2 > hend + A.bc_len + 1) why = 0;
                         }
                     }
                     if (why == 3) why = fasta_eval(B, A.nbytes, p + 1, hend, A.bc_len, A.packed, key);

@@ -334,3 +334,78 @@ def test_reads_with_invalid_bases_in_the_window(gpu, k, n_bc, m):
         out += b"@r%d\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n"
     for flags in (0, gpu["ffi"].CFG_NO_LUT):
         _check_against_oracle(gpu, bytes(out), bcs, m, batch_bytes=1 << 20, flags=flags)
+
+
+# ---- irregular records across many scan regions ------------------------------------------------------------------
+@pytest.mark.parametrize("fmt,seed", [("fastq", 1), ("fastq", 2), ("fasta", 3)])
+def test_irregular_records_many_regions(gpu, fmt, seed):
+    """~25 MB in ONE batch (hundreds of 36 KB tiles, a region per CTA): read lengths 30-400, a sprinkle of CRLF records,
+    '+id' separator lines, N / lower-case bases, multi-line FASTA -- region starts land in every kind of line"""
+    rng = random.Random(seed)
+    bcs = [bytes(rng.choice(b"ACGT") for _ in range(7)) for _ in range(60)]
+    parts = []
+    size = 0
+    i = 0
+    while size < 25_000_000:
+        L = rng.randint(30, 400)
+        pre = bytearray(rng.choice(bcs)) if rng.random() < 0.8 else bytearray(rng.choice(b"ACGT") for _ in range(7))
+        if rng.random() < 0.3:
+            pre[rng.randrange(7)] = rng.choice(b"ACGTNa")
+        s = bytes(pre) + bytes(rng.choice(b"ACGT") for _ in range(L))
+        odd = rng.random() < 0.01
+        nl = b"\r\n" if odd and rng.random() < 0.5 else b"\n"
+        if fmt == "fastq":
+            q = bytes(rng.randint(33, 73) for _ in range(len(s)))
+            sep = (b"+r%d" % i) if odd else b"+"
+            rec = b"@r%d len=%d" % (i, L) + nl + s + nl + sep + nl + q + nl
+        else:
+            if odd:
+                w = rng.randint(5, 60)
+                body = nl.join(s[j:j + w] for j in range(0, len(s), w))
+            else:
+                body = s
+            rec = b">r%d len=%d" % (i, L) + nl + body + nl
+        parts.append(rec)
+        size += len(rec)
+        i += 1
+    text = b"".join(parts)
+    _check_against_oracle(gpu, text, bcs, 1, batch_bytes=32 << 20, chunk=4 << 20)
+
+
+@pytest.mark.parametrize("crlf", [False, True])
+@pytest.mark.parametrize("width_delta", [-2, -1, 0, 1, 2])
+def test_fasta_line_width_around_the_match_window(gpu, crlf, width_delta):
+    """sequence lines exactly as wide as the match window, one less, one more ...: with CR LF the CR sits right where a
+    base of the window would be"""
+    rng = random.Random(100 + width_delta + (7 if crlf else 0))
+    k = 9
+    bcs = [bytes(rng.choice(b"ACGT") for _ in range(k)) for _ in range(50)]
+    nl = b"\r\n" if crlf else b"\n"
+    w = k + width_delta
+    out = bytearray()
+    for i in range(30000):
+        pre = bytearray(rng.choice(bcs))
+        if rng.random() < 0.4:
+            pre[rng.randrange(k)] = rng.choice(b"ACGTN")
+        s = bytes(pre) + bytes(rng.choice(b"ACGT") for _ in range(rng.randint(0, 40)))
+        wi = w if rng.random() < 0.7 else rng.randint(3, 50)
+        out += b">s%d" % i + nl + nl.join(s[j:j + wi] for j in range(0, len(s), wi)) + nl
+    _check_against_oracle(gpu, bytes(out), bcs, 1, batch_bytes=4 << 20, chunk=1 << 20)
+
+
+def test_fastq_many_odd_records(gpu):
+    """every tenth record needs the general evaluation (CR LF, '+id', N): the out-of-line path next to the fast one"""
+    rng = random.Random(77)
+    bcs = [bytes(rng.choice(b"ACGT") for _ in range(8)) for _ in range(30)]
+    out = bytearray()
+    for i in range(60000):
+        L = rng.randint(8, 200)
+        pre = bytearray(rng.choice(bcs))
+        if rng.random() < 0.3:
+            pre[rng.randrange(8)] = rng.choice(b"ACGTNn")
+        s = bytes(pre) + bytes(rng.choice(b"ACGT") for _ in range(L - 8))
+        q = bytes(rng.randint(33, 73) for _ in range(L))
+        odd = rng.random() < 0.1
+        nl = b"\r\n" if odd and rng.random() < 0.5 else b"\n"
+        out += b"@q%d" % i + nl + s + nl + ((b"+q%d" % i) if odd else b"+") + nl + q + nl
+    _check_against_oracle(gpu, bytes(out), bcs, 2, batch_bytes=8 << 20, chunk=1 << 20)

@@ -6,14 +6,15 @@
 // Why not a global prefix scan: a single-pass decoupled look-back over 12 KB tiles resolves at most
 // 32 tiles per L2 round trip, which caps a newline-count scan near 0.45 TB/s on B200 (measured, see
 // DESIGN.md).  Here nothing on the critical path waits on another CTA:
-//   * the batch is cut into one contiguous region per CTA; the CTA streams its region tile by tile
-//     through a ring of 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP) completing on mbarriers;
-//   * inside a tile every WARP owns a contiguous 3 KB slice: it builds the newline masks of its slice,
+//   * the batch is cut into one contiguous region per CTA; the CTA streams its region tile by tile with 1-D bulk
+//     async copies (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier; the tile after the one being loaded
+//     is pulled into L2 with a bulk prefetch, so that the single-buffered stage waits for an L2 hit only;
+//   * inside a tile every WARP owns a contiguous 4.5 KB slice: it builds the newline masks of its slice,
 //     compacts the newline positions into a warp-private list and evaluates the records that END in
-//     its slice, one lane per record.  The only things a warp needs from the others are how many
+//     its slice, two lanes per record.  The only things a warp needs from the others are how many
 //     newlines precede its slice (its place in the 4-line cycle) and the last four newline positions
-//     before it; both are published before the ONE block barrier of the tile, so every warp carries
-//     the same load between barriers;
+//     before it; both are published before the tile's barrier, so every warp carries the same load
+//     between barriers;
 //   * FASTQ: where in the 4-line cycle a region starts is not known locally ('@' and '+' are legal
 //     quality characters), so the CTA DETECTS it from its first eight newlines (the one phase under
 //     which the first whole record parses) and k_scan_finish VERIFIES every region's phase against the
@@ -26,8 +27,6 @@
 //   * per record: validate ('+' line, equal lengths, CR, next record's '@'), 2-bit pack the first bc_len
 //     bases, write seg_rec_off / seg_key at the region-local index.  The match kernel compacts the
 //     per-region segments into dense arrays while it reads the keys.
-#include <cstdlib>
-
 #include "scan_common.cuh"
 
 namespace sbr {
@@ -726,8 +725,7 @@ __global__ void __launch_bounds__(MAX_REGIONS) k_scan_finish(BatchHeader* hdr, R
 }  // namespace
 
 size_t scan_fast_smem_bytes(uint32_t fmt) {
-    static const size_t pad = getenv("SBR_SCAN_PAD_SMEM") ? (size_t)atoi(getenv("SBR_SCAN_PAD_SMEM")) : 0;  // occupancy experiments
-    return pad + (size_t)FAST_STAGES * stage_stride((int)fmt) +
+    return (size_t)FAST_STAGES * stage_stride((int)fmt) +
            (fmt == SBR_FMT_FASTA ? sizeof(FastSmem<SBR_FMT_FASTA>) : sizeof(FastSmem<SBR_FMT_FASTQ>));
 }
 

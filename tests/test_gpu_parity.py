@@ -213,9 +213,10 @@ def test_edge_inputs(gpu, kind, m, big):
     assert sum(len(o) for o in outs_exp) > 0
 
 
-@pytest.mark.parametrize("batch", [1 << 12, 12288, 12288 + 16, 3 * 12288 - 1, 50_000])
+@pytest.mark.parametrize("batch", [1 << 12, 4608, 12288, 12288 + 16, 3 * 12288 - 1, 36864, 36864 + 16, 2 * 36864 - 1, 50_000,
+                                   4 * 36864 + 48])
 def test_batch_and_tile_boundaries(gpu, batch):
-    """records straddle tiles (12 KB) and batches at every alignment"""
+    """records straddle warp slices (4.5 KB), tiles (36 KB; 12 KB in the look-back scan) and batches at every alignment"""
     rng = random.Random(batch)
     text = _rand_fastq(rng, 2500, lo=30, hi=200)
     bcs = [bytes(rng.choice(b"ACGT") for _ in range(6)) for _ in range(20)]

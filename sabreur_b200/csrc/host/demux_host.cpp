@@ -603,13 +603,46 @@ std::pair<Counts&, std::string> pe_demux(const std::string& forward, const std::
     if (format != Format::No) compression = format;
     const auto bcs = barcode_list(bd);
     if (bd.unknown.size() < 2) throw std::runtime_error("Missing 'XXX' fallback barcode entry in barcode_data");
-    bool unk[2];
-    for (int mate = 0; mate < 2; ++mate) {  // forward pass, then reverse pass (demux.rs:101-110, 114-123)
-        std::vector<FILE*> files;
-        for (auto& r : bd.rows) files.push_back(r.files.at(mate).fh);
-        files.push_back(bd.unknown.at(mate).fh);
-        Pass pass(mate == 0 ? forward : reverse, files, bcs, mismatch, compression, level, opt, stats);
-        unk[mate] = pass.run(/*strict=*/false, nb_records, bcs);
+    // The reference runs the forward pass, then the reverse pass (demux.rs:101-110, 114-123).  The mates are
+    // independent streams writing to disjoint files, so both passes may run at once (each with its own contexts):
+    // with compressed inputs the single-threaded inflate of each file is the wall, and two of them run in parallel.
+    bool unk[2] = {true, true};
+    Counts counts[2];
+    RunStats st[2];
+    std::exception_ptr errs[2];
+    auto run_mate = [&](int mate) {
+        try {
+            std::vector<FILE*> files;
+            for (auto& r : bd.rows) files.push_back(r.files.at(mate).fh);
+            files.push_back(bd.unknown.at(mate).fh);
+            Pass pass(mate == 0 ? forward : reverse, files, bcs, mismatch, compression, level, opt, stats ? &st[mate] : nullptr);
+            unk[mate] = pass.run(/*strict=*/false, counts[mate], bcs);
+        } catch (...) {
+            errs[mate] = std::current_exception();
+        }
+    };
+    if (opt.parallel_mates) {
+        std::thread t1([&] { run_mate(1); });
+        run_mate(0);
+        t1.join();
+    } else {
+        run_mate(0);
+        if (!errs[0]) run_mate(1);
+    }
+    for (int mate = 0; mate < 2; ++mate)
+        if (errs[mate]) std::rethrow_exception(errs[mate]);
+    for (int mate = 0; mate < 2; ++mate) {  // forward counts first, then reverse: the order the sequential passes add them
+        for (auto& kv : counts[mate]) {
+            auto it = std::find_if(nb_records.begin(), nb_records.end(), [&](auto& p) { return p.first == kv.first; });
+            if (it == nb_records.end()) nb_records.push_back(kv);
+            else it->second += kv.second;
+        }
+        if (stats) {
+            stats->read_s += st[mate].read_s; stats->gpu_wait_s += st[mate].gpu_wait_s; stats->write_s += st[mate].write_s;
+            stats->total_s = std::max(stats->total_s, st[mate].total_s) + (opt.parallel_mates ? 0.0 : (mate ? st[0].total_s : 0.0));
+            stats->bytes_in += st[mate].bytes_in; stats->records += st[mate].records; stats->batches += st[mate].batches;
+            stats->respeculated += st[mate].respeculated;
+        }
     }
     return {nb_records, std::string(unk[0] ? "true" : "false") + (unk[1] ? "true" : "false")};
 }

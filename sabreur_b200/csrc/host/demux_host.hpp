@@ -48,6 +48,7 @@ struct HostOptions {
     uint64_t batch_bytes = 256ull << 20;
     uint32_t slots_per_gpu = 2;
     int writer_threads = 0;         // 0 = hardware concurrency (capped)
+    bool parallel_mates = true;     // paired-end: run the forward and the reverse pass at the same time
     bool verbose = false;
 };
 

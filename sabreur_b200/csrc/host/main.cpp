@@ -12,6 +12,7 @@
 //         --gpus <N>       deal batches round-robin to N GPUs [1]
 //         --batch-mb <N>   size of one GPU batch in MiB [256]
 //         --timing         print where the wall time went
+//         --sequential-mates   paired-end: one pass after the other, like the reference (default: both at once)
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -108,6 +109,7 @@ void print_help() {
          "      --gpus <N>             Number of GPUs batches are dealt to [default: 1]\n"
          "      --batch-mb <N>         GPU batch size in MiB [default: 256]\n"
          "      --timing               Report where the wall time went\n"
+         "      --sequential-mates     Paired-end: run the reverse pass after the forward pass (default: both at once)\n"
          "  -h, --help                 Print help\n"
          "  -V, --version              Print version\n\n"
          "Note: `sabreur -h` prints a short and concise overview while `sabreur --help` gives all details.");
@@ -121,7 +123,7 @@ struct Cli {
     bool has_format = false;
     Format format = Format::No;
     int level = 1;
-    bool force = false, quiet = false, timing = false;
+    bool force = false, quiet = false, timing = false, sequential_mates = false;
     int gpus = 1;
     int batch_mb = 256;
 };
@@ -169,6 +171,7 @@ Cli parse_cli(int argc, char** argv) {
         else if (key == "--force") c.force = true;
         else if (key == "-q" || key == "--quiet") c.quiet = true;
         else if (key == "--timing") c.timing = true;
+        else if (key == "--sequential-mates") c.sequential_mates = true;
         else if (key == "--gpus") c.gpus = std::max(1, atoi(value(i, key, inl)));
         else if (key == "--batch-mb") c.batch_mb = std::max(1, atoi(value(i, key, inl)));
         else if (a.size() > 1 && a[0] == '-') usage_error("unexpected argument '" + a + "' found");
@@ -243,6 +246,7 @@ int main(int argc, char** argv) {
         HostOptions opt;
         opt.n_gpus = cli.gpus;
         opt.batch_bytes = (uint64_t)cli.batch_mb << 20;
+        opt.parallel_mates = !cli.sequential_mates;
         RunStats rs;
         std::string unknown_paths[2];
 

@@ -297,8 +297,22 @@ def _read_chunks(path: str, chunk: int = 4 << 20) -> Iterator[bytes]:
             yield b
 
 
+def _member(data: bytes, fmt: str, level: int) -> bytes:
+    """one compressed member holding `data` (members concatenate into a valid file; the reference writes one member
+    per record through niffler::get_writer, src/utils.rs:139 -- same decompressed content)"""
+    if fmt == "":
+        return data
+    if fmt == ".gz":
+        return gzip.compress(data, compresslevel=level)
+    if fmt == ".bz2":
+        return bz2.compress(data, compresslevel=level)
+    if fmt == ".xz":
+        return lzma.compress(data, preset=level)
+    raise SabreurGpuError("zstd output needs the C++ host (no zstd module in this Python)")
+
+
 def _demux_one(path: str, writers: list, unknown_writer, barcodes: list[bytes], mismatch: int,
-               nb_records: dict, strict: bool, **kw) -> bool:
+               nb_records: dict, strict: bool, fmt: str = "", level: int = 1, **kw) -> bool:
     """one pass of the hot loop (src/demux.rs:49-66 / 101-110 / 114-123). -> is_unk_empty"""
     unk_empty = True
     with Demux(barcodes, mismatch, **kw) as dm:
@@ -316,11 +330,13 @@ def _demux_one(path: str, writers: list, unknown_writer, barcodes: list[bytes], 
                     unk_empty = False
                 else:
                     nb_records[barcodes[bin_]] = nb_records.get(barcodes[bin_], 0) + int(seg.size)
+                parts = []
                 for i in seg:
                     rec = text[b.rec_off[i]: b.rec_off[i + 1]].tobytes()
                     if noncanon and (b.fmt == FMT_FASTA or (int(b.rec_key[i]) & _ffi.KEY_NONCANON)):
                         rec = _canonical(rec, b.fmt)
-                    w.write(rec)
+                    parts.append(rec)
+                w.write(_member(b"".join(parts), fmt, level))
             if b.status & _ffi.ST_ERROR_MASK:
                 if b.first_bad_flags & _ffi.ST_SHORT_READ:
                     raise ParseError(b.first_bad_flags, b.record_base + b.first_bad_record)  # slice panic, demux.rs:54
@@ -330,23 +346,41 @@ def _demux_one(path: str, writers: list, unknown_writer, barcodes: list[bytes], 
     return unk_empty
 
 
-def se_demux(file: str, barcode_data: dict, mismatch: int, nb_records: dict, **kw):
-    """src/demux.rs:13-67.  barcode_data: {barcode bytes: [writable binary file]} in barcode-file order,
-    with the b"XXX" entry holding the unknown writer (src/main.rs:152-158).  -> (nb_records, is_unk_empty)"""
+_LEVELS = {1, 2, 3, 4, 5, 6, 7, 8, 9}
+
+
+def se_demux(file: str, format: str, level: int, barcode_data: dict, mismatch: int, nb_records: dict, **kw):
+    """src/demux.rs:13-67, same argument order.  `format`: "" (niffler Format::No: keep the input's compression),
+    ".gz", ".bz2", ".xz" (".zst" needs the C++ host); `level` 1-9 (utils.rs:87-100: anything else -> 1).
+    barcode_data: {barcode bytes: [writable binary file]} in barcode-file order, with the b"XXX" entry holding the
+    unknown writer (src/main.rs:152-158).  -> (nb_records, is_unk_empty)"""
     if not barcode_data:
         raise ValueError("Barcode data is empty")
     if b"XXX" not in barcode_data:
         raise ValueError("Missing 'XXX' fallback barcode entry in barcode_data")
+    if format == "":
+        format = which_format(file)  # demux.rs:26-29
+    level = level if level in _LEVELS else 1
     bcs = [k for k in barcode_data if k != b"XXX"]
     writers = [barcode_data[k][0] for k in bcs]
-    unk = _demux_one(file, writers, barcode_data[b"XXX"][0], bcs, mismatch, nb_records, strict=True, **kw)
+    unk = _demux_one(file, writers, barcode_data[b"XXX"][0], bcs, mismatch, nb_records, strict=True, fmt=format, level=level,
+                     **kw)
     return nb_records, unk
 
 
-def pe_demux(forward: str, reverse: str, barcode_data: dict, mismatch: int, nb_records: dict, **kw):
-    """src/demux.rs:71-128: two independent passes, forward then reverse.  -> (nb_records, "truetrue"...)"""
+def pe_demux(forward: str, reverse: str, format: str, level: int, barcode_data: dict, mismatch: int, nb_records: dict,
+             **kw):
+    """src/demux.rs:71-128: two independent passes, forward then reverse; both mates are written with the
+    forward-derived compression unless `format` is given (demux.rs:81,95-97).  -> (nb_records, "truetrue"...)"""
+    compression = which_format(forward)
+    which_format(reverse)
+    if format != "":
+        compression = format
+    level = level if level in _LEVELS else 1
     bcs = [k for k in barcode_data if k != b"XXX"]
     unk = barcode_data[b"XXX"]
-    u1 = _demux_one(forward, [barcode_data[k][0] for k in bcs], unk[0], bcs, mismatch, nb_records, strict=False, **kw)
-    u2 = _demux_one(reverse, [barcode_data[k][1] for k in bcs], unk[1], bcs, mismatch, nb_records, strict=False, **kw)
+    u1 = _demux_one(forward, [barcode_data[k][0] for k in bcs], unk[0], bcs, mismatch, nb_records, strict=False,
+                    fmt=compression, level=level, **kw)
+    u2 = _demux_one(reverse, [barcode_data[k][1] for k in bcs], unk[1], bcs, mismatch, nb_records, strict=False,
+                    fmt=compression, level=level, **kw)
     return nb_records, f"{str(u1).lower()}{str(u2).lower()}"

@@ -34,7 +34,11 @@ namespace sbr {
 namespace {
 
 constexpr uint32_t UNKNOWN_L = 0xFFFFFFFFu;
-constexpr int FAST_WARPS = SCAN_THREADS / 32;
+#ifndef SBR_FAST_WARPS
+#define SBR_FAST_WARPS 8
+#endif
+constexpr int FAST_WARPS = SBR_FAST_WARPS;  // warps (= slices of a tile) per CTA
+constexpr int FAST_THREADS = FAST_WARPS * 32;
 // A lane masks 48 bytes in each of FAST_UNITS units of its warp's slice; one warp scan serves all of them.
 // Two geometries (SBR_SCAN_SINGLE selects at compile time):
 //   double-buffered: 2 units per lane, 3 KB slices, 24 KB tiles, two stages (the next tile loads while this one is scanned)
@@ -199,7 +203,7 @@ __device__ __noinline__ uint64_t fastq_slow(const uint8_t* sm, const uint8_t* te
 
 // KW: 32-bit words of text covering the match window (ceil(bc_len / 4), 1..4) in packed mode; 0 = unpacked keys
 template <int FMT, int KW>
-__global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_fast(FastArgs A) {
+__global__ void __launch_bounds__(FAST_THREADS, 4) k_scan_fast(FastArgs A) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     constexpr int STAGE_STRIDE = stage_stride(FMT);
     uint8_t* stage_buf = dyn_smem + (STAGE_STRIDE - FAST_TILE);  // stage s = stage_buf + s * STAGE_STRIDE, its tail pad right before it
@@ -755,7 +759,7 @@ cudaError_t scan_fast_prepare(int device, int* grid_fastq, int* grid_fasta) {
                 cudaSuccess)
                 return e;
             int r = 0;
-            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k, SCAN_THREADS, scan_fast_smem_bytes(fmt))) != cudaSuccess)
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k, FAST_THREADS, scan_fast_smem_bytes(fmt))) != cudaSuccess)
                 return e;
             int& best = resident[fmt - SBR_FMT_FASTA];
             best = r < best ? r : best;
@@ -808,11 +812,11 @@ cudaError_t scan_fast_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbyte
     A.seg_key = seg_key;
     size_t smem = scan_fast_smem_bytes(fmt);
     if (fmt == SBR_FMT_FASTQ) {
-        fast_kernel<SBR_FMT_FASTQ>(bc_len, packed)<<<n_regions, SCAN_THREADS, smem, stream>>>(A);
+        fast_kernel<SBR_FMT_FASTQ>(bc_len, packed)<<<n_regions, FAST_THREADS, smem, stream>>>(A);
         k_scan_finish<SBR_FMT_FASTQ><<<1, MAX_REGIONS, 0, stream>>>(hdr, info, n_regions, nbytes, max_records, final_batch,
                                                                     region_base, rec_off_dense, lookback_desc, n_desc);
     } else {
-        fast_kernel<SBR_FMT_FASTA>(bc_len, packed)<<<n_regions, SCAN_THREADS, smem, stream>>>(A);
+        fast_kernel<SBR_FMT_FASTA>(bc_len, packed)<<<n_regions, FAST_THREADS, smem, stream>>>(A);
         k_scan_finish<SBR_FMT_FASTA><<<1, MAX_REGIONS, 0, stream>>>(hdr, info, n_regions, nbytes, max_records, final_batch,
                                                                     region_base, rec_off_dense, lookback_desc, n_desc);
     }

@@ -105,6 +105,8 @@ struct Slot {
     cudaStream_t last_stream = nullptr;
     bool via_submit = false;  // results' header copy already queued behind hdr_ready
     bool supplied_nl = false; // the final newline of the stream was missing and has been supplied
+    const uint8_t* cur_text = nullptr;  // device text of the batch in flight (for a re-run through the exact scan)
+    uint32_t cur_cap_r = 0;
 };
 
 }  // namespace
@@ -360,51 +362,69 @@ extern "C" int sbr_slot_buffer(sbr_ctx* c, uint32_t slot, uint8_t** host_ptr, ui
 }
 
 // scan -> match -> partition on `st`
-static int launch_pipeline(sbr_ctx* c, Slot& s, const uint8_t* d_text, uint32_t nbytes, uint32_t fmt, int final_batch,
-                           cudaStream_t st) {
-    cudaEvent_t* ev = nullptr;
-    if (c->timing && c->ev_used < TIMING_RING) ev = &c->ev[(size_t)c->ev_used++ * 4];
-    CU(c, cudaMemsetAsync(s.d_hdr, 0, sizeof(BatchHeader), st));
-    // the look-back scan's tile descriptors: zeroed here only when that scan is forced; otherwise k_scan_finish clears
-    // them in the rare case it hands the batch over
-    if (c->exact_only) CU(c, cudaMemsetAsync(s.d_desc, 0, (size_t)scan_tiles(nbytes) * sizeof(uint4), st));
-    if (ev) CU(c, cudaEventRecord(ev[0], st));
-    uint32_t cap_r = 0;
-    if (!c->exact_only) {
-        uint32_t tpr = 0, extra = 0;
-        uint32_t nreg = scan_fast_regions(nbytes, fmt == SBR_FMT_FASTA ? c->fast_grid_a : c->fast_grid_q, &tpr, &extra);
-        // segments get 25 % + 64 records of slack over an even split: regions hold unequal record counts
-        cap_r = (uint32_t)(((uint64_t)c->max_records * 5 / 4) / nreg) + 64;
-        CU(c, scan_fast_launch(fmt, d_text, nbytes, c->max_records, cap_r, nreg, tpr, extra, c->cfg.bc_len, c->packed ? 1u : 0u,
-                               (uint32_t)final_batch, s.d_hdr, s.d_info, s.d_region_base, s.d_seg_rec_off, s.d_seg_key,
-                               s.d_rec_off, s.d_desc, scan_tiles(nbytes), st));
-        c->launches += 2;
-    }
-    // the look-back scan: unconditional when forced, otherwise it returns at once unless the fast scan gave up
-    CU(c, scan_launch(fmt, d_text, nbytes, c->max_records, c->cfg.bc_len, c->packed ? 1u : 0u, (uint32_t)final_batch,
-                      c->exact_only ? 0u : 1u, s.d_hdr, s.d_desc, s.d_rec_off, s.d_key, c->scan_grid, st));
-    if (ev) CU(c, cudaEventRecord(ev[1], st));
-    {
-        MatchLaunch L{};
-        L.key_dense = s.d_key; L.seg_key = s.d_seg_key; L.seg_rec_off = s.d_seg_rec_off; L.region_base = s.d_region_base;
-        L.cap_r = cap_r;
-        L.hdr = s.d_hdr;
-        L.tab = c->packed ? c->d_tab : nullptr; L.lut = c->d_lut; L.lut1 = c->d_lut1; L.uniform = c->uniform ? 1u : 0u; L.rows = c->d_rows; L.lens = c->d_lens;
-        L.n = c->cfg.n_barcodes; L.m = c->cfg.mismatch; L.k = c->cfg.bc_len; L.stride = c->cfg.bc_len;
-        L.text = d_text; L.nbytes = nbytes;
-        L.assign = s.d_assign; L.rec_off = s.d_rec_off; L.key_out = s.d_key; L.cta_cnt = s.d_cta_cnt; L.nbins = c->nbins;
-        L.grid = c->plan.grid;
-        L.fused = c->fused ? 1 : 0; L.nbits = c->plan.nbits;
-        L.bin_count = s.d_bin_count; L.bin_start = s.d_bin_start; L.order = s.d_order;
-        CU(c, match_launch(L, st));
-    }
+// match (+ partition) over whatever scan result the header describes, on `st`
+static int launch_match_partition(sbr_ctx* c, Slot& s, const uint8_t* d_text, uint32_t nbytes, uint32_t cap_r, cudaStream_t st,
+                                  cudaEvent_t* ev) {
+    MatchLaunch L{};
+    L.key_dense = s.d_key; L.seg_key = s.d_seg_key; L.seg_rec_off = s.d_seg_rec_off; L.region_base = s.d_region_base;
+    L.cap_r = cap_r;
+    L.hdr = s.d_hdr;
+    L.tab = c->packed ? c->d_tab : nullptr; L.lut = c->d_lut; L.lut1 = c->d_lut1; L.uniform = c->uniform ? 1u : 0u;
+    L.rows = c->d_rows; L.lens = c->d_lens;
+    L.n = c->cfg.n_barcodes; L.m = c->cfg.mismatch; L.k = c->cfg.bc_len; L.stride = c->cfg.bc_len;
+    L.text = d_text; L.nbytes = nbytes;
+    L.assign = s.d_assign; L.rec_off = s.d_rec_off; L.key_out = s.d_key; L.cta_cnt = s.d_cta_cnt; L.nbins = c->nbins;
+    L.grid = c->plan.grid;
+    L.fused = c->fused ? 1 : 0; L.nbits = c->plan.nbits;
+    L.bin_count = s.d_bin_count; L.bin_start = s.d_bin_start; L.order = s.d_order;
+    CU(c, match_launch(L, st));
     if (ev) CU(c, cudaEventRecord(ev[2], st));
     if (!c->fused)
         CU(c, partition_launch(s.d_assign, s.d_hdr, c->nbins, s.d_cta_cnt, s.d_bin_count, s.d_bin_start, s.d_order,
                                s.d_done, c->plan, st));
     if (ev) CU(c, cudaEventRecord(ev[3], st));
-    c->launches += (fmt == SBR_FMT_FASTA ? 2 : 1) + 1 + (c->fused ? 0 : 2);  // look-back scan (+finish), match, partition
+    c->launches += 1 + (c->fused ? 0 : 2);
     return SBR_OK;
+}
+
+// scan -> match -> partition on `st`.  The region-parallel scan is launched optimistically: when it hands a batch
+// over (hdr->spec_fail: malformed, newline-dense, undecidable ...) the header says "no records", match and partition
+// run over nothing, and sbr_wait() re-runs the batch through the exact look-back scan (rerun_exact below).  A clean
+// batch therefore never pays for a launch of the fallback.
+static int launch_pipeline(sbr_ctx* c, Slot& s, const uint8_t* d_text, uint32_t nbytes, uint32_t fmt, int final_batch,
+                           cudaStream_t st) {
+    cudaEvent_t* ev = nullptr;
+    if (c->timing && c->ev_used < TIMING_RING) ev = &c->ev[(size_t)c->ev_used++ * 4];
+    CU(c, cudaMemsetAsync(s.d_hdr, 0, sizeof(BatchHeader), st));
+    s.cur_text = d_text;
+    s.cur_cap_r = 0;
+    if (ev) CU(c, cudaEventRecord(ev[0], st));
+    if (c->exact_only) {
+        CU(c, cudaMemsetAsync(s.d_desc, 0, (size_t)scan_tiles(nbytes) * sizeof(uint4), st));
+        CU(c, scan_launch(fmt, d_text, nbytes, c->max_records, c->cfg.bc_len, c->packed ? 1u : 0u, (uint32_t)final_batch, 0u,
+                          s.d_hdr, s.d_desc, s.d_rec_off, s.d_key, c->scan_grid, st));
+        c->launches += (fmt == SBR_FMT_FASTA ? 2 : 1);
+    } else {
+        uint32_t tpr = 0, extra = 0;
+        uint32_t nreg = scan_fast_regions(nbytes, fmt == SBR_FMT_FASTA ? c->fast_grid_a : c->fast_grid_q, &tpr, &extra);
+        // segments get 25 % + 64 records of slack over an even split: regions hold unequal record counts
+        s.cur_cap_r = (uint32_t)(((uint64_t)c->max_records * 5 / 4) / nreg) + 64;
+        // (k_scan_finish clears the look-back scan's tile descriptors when it hands the batch over)
+        CU(c, scan_fast_launch(fmt, d_text, nbytes, c->max_records, s.cur_cap_r, nreg, tpr, extra, c->cfg.bc_len,
+                               c->packed ? 1u : 0u, (uint32_t)final_batch, s.d_hdr, s.d_info, s.d_region_base, s.d_seg_rec_off,
+                               s.d_seg_key, s.d_rec_off, s.d_desc, scan_tiles(nbytes), st));
+        c->launches += 2;
+    }
+    if (ev) CU(c, cudaEventRecord(ev[1], st));
+    return launch_match_partition(c, s, d_text, nbytes, s.cur_cap_r, st, ev);
+}
+
+// the region-parallel scan handed the batch over: exact look-back scan, then match and partition again
+static int rerun_exact(sbr_ctx* c, Slot& s, cudaStream_t st) {
+    CU(c, scan_launch(s.fmt, s.cur_text, s.nbytes_eff, c->max_records, c->cfg.bc_len, c->packed ? 1u : 0u,
+                      (uint32_t)s.final_batch, 1u, s.d_hdr, s.d_desc, s.d_rec_off, s.d_key, c->scan_grid, st));
+    c->launches += (s.fmt == SBR_FMT_FASTA ? 2 : 1);
+    return launch_match_partition(c, s, s.cur_text, s.nbytes_eff, s.cur_cap_r, st, nullptr);
 }
 
 static uint32_t sniff_fmt(const sbr_ctx* c, uint8_t first) {
@@ -547,6 +567,14 @@ extern "C" int sbr_wait(sbr_ctx* c, uint32_t slot, sbr_result* r) {
     if (s.via_submit) {
         CU(c, cudaEventSynchronize(s.hdr_ready));
     } else {  // device-resident batch: fetch the small results now
+        CU(c, cudaMemcpyAsync(s.h_hdr, s.d_hdr, sizeof(BatchHeader), cudaMemcpyDeviceToHost, st));
+        CU(c, cudaMemcpyAsync(s.h_bin_count, s.d_bin_count, c->nbins * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(c, cudaMemcpyAsync(s.h_bin_start, s.d_bin_start, (c->nbins + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st));
+    }
+    if (s.h_hdr->spec_fail && !c->exact_only) {  // rare: the optimistic scan gave up, the exact one takes the batch
+        rc = rerun_exact(c, s, st);
+        if (rc) return rc;
         CU(c, cudaMemcpyAsync(s.h_hdr, s.d_hdr, sizeof(BatchHeader), cudaMemcpyDeviceToHost, st));
         CU(c, cudaMemcpyAsync(s.h_bin_count, s.d_bin_count, c->nbins * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CU(c, cudaMemcpyAsync(s.h_bin_start, s.d_bin_start, (c->nbins + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));

@@ -127,7 +127,10 @@ int sbr_wait(sbr_ctx* ctx, uint32_t slot, sbr_result* res);
  * Runs scan -> match -> partition on text that already lives in device memory (16-byte aligned),
  * on `stream` (a cudaStream_t passed as void*; NULL = the slot's own stream), using the slot's
  * device workspace.  Nothing is copied by the call itself: sbr_slot_device_result() exposes the
- * DEVICE pointers, and a following sbr_wait() on the slot copies the results to pinned host memory. */
+ * DEVICE pointers, and a following sbr_wait() on the slot copies the results to pinned host memory.
+ * d_text must be readable up to the next multiple of 16 bytes past nbytes.  The device results are final
+ * only after sbr_wait(): a batch the region-parallel scan hands over (malformed, newline-dense ...) reads
+ * "no records" until sbr_wait() has re-run it through the exact scan. */
 int sbr_demux_device(sbr_ctx* ctx, uint32_t slot, const uint8_t* d_text, uint64_t nbytes,
                      int final_batch, void* stream);
 int sbr_slot_device_result(sbr_ctx* ctx, uint32_t slot, sbr_result* res_device_ptrs);

@@ -72,6 +72,7 @@ struct FastSmem {
     uint32_t wtot[2][FAST_WARPS];           // by tile parity: newlines | record starts << 16 of each warp slice
     uint32_t wtail[2][FAST_WARPS][GHOSTS];  // by tile parity: the slice's last four newline positions, [0] most recent
     uint32_t whead[2][FAST_WARPS][2];       // by tile parity: the slice's first two newline positions (FASTA looks ahead)
+    uint16_t ridx[FMT == SBR_FMT_FASTA ? FAST_WARPS : 1][FMT == SBR_FMT_FASTA ? WL_CAP + 4 : 2];  // FASTA: list index of the u-th record start
     uint32_t gh[2][GHOSTS];                 // by tile parity: the four most recent newlines before the tile
     uint32_t cnt[2];                        // newlines of the region before the tile
     uint32_t rcnt[2];                       // FASTA: record starts of the region before the tile
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_scan_fast(FastArgs A) {
                         if (st) wl[GHOSTS + jx] = pos | FASTA_START;
                     }
                     start_bal[ch] = __ballot_sync(0xFFFFFFFFu, st);
+                    if (st) S.ridx[warp][nr_w + __popc(start_bal[ch] & ((1u << lane) - 1u))] = (uint16_t)jx;  // rank -> list index
                     nr_w += __popc(start_bal[ch]);
                 }
                 if (crlf) S.crlf = 1;
@@ -560,13 +562,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_scan_fast(FastArgs A) {
             // lane u takes the u-th flagged entry (every other newline of single-line FASTA is a start: going chunk by
             // chunk would leave half of the lanes idle in twice as many passes)
             for (uint32_t u = (uint32_t)lane; fits && u < nr_w; u += 32u) {
-                uint32_t idx = 0, rem = u;
-#pragma unroll
-                for (int ch = 0; ch < FASTA_CHUNKS; ++ch) {
-                    const uint32_t cch = __popc(start_bal[ch]);
-                    if (rem < cch) { idx = ch * 32 + __fns(start_bal[ch], 0u, (int)rem + 1); break; }
-                    rem -= cch;
-                }
+                const uint32_t idx = S.ridx[warp][u];
                 {
                     const uint32_t p = wl[GHOSTS + idx] & POS_MASK;
                     // the two newlines behind the record start (the header's, the first sequence line's): from the own

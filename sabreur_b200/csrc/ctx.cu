@@ -36,7 +36,7 @@ struct MatchLaunch {
     const uint8_t* text; uint32_t nbytes;
     uint16_t* assign; uint32_t* rec_off; uint64_t* key_out; uint32_t* cta_cnt; uint32_t nbins;
     int grid;
-    int fused; uint32_t nbits; uint32_t* bin_count; uint32_t* bin_start; uint32_t* order;
+    int fused; uint32_t nbits; uint32_t* bin_count; uint32_t* bin_start; uint32_t* order; BatchHeader* zero_next;
 };
 size_t match_smem(uint32_t n, uint32_t stride, uint32_t nbins, bool generic);
 cudaError_t match_prepare();
@@ -54,7 +54,7 @@ PartitionPlan partition_plan(uint32_t nbins, uint32_t max_records, int sms);
 cudaError_t partition_prepare();
 cudaError_t partition_launch(const uint16_t* d_assign, const BatchHeader* d_hdr, uint32_t nbins,
                              uint32_t* d_cta_cnt, uint32_t* d_bin_count, uint32_t* d_bin_start, uint32_t* d_order,
-                             uint32_t* d_done_counter, const PartitionPlan& p, cudaStream_t stream);
+                             uint32_t* d_done_counter, BatchHeader* d_zero_next, const PartitionPlan& p, cudaStream_t stream);
 }  // namespace sbr
 
 using namespace sbr;
@@ -70,7 +70,9 @@ struct Slot {
     cudaEvent_t hdr_ready = nullptr;
     // device
     uint8_t* d_text = nullptr;
-    BatchHeader* d_hdr = nullptr;
+    BatchHeader* d_hdr = nullptr;   // the header of the batch in flight: one of d_hdr2[0..1], alternating
+    BatchHeader* d_hdr2 = nullptr;  // both start out zeroed; the last kernel of a batch clears the other one for the next batch
+    uint32_t hdr_idx = 0;
     uint4* d_desc = nullptr;
     uint32_t* d_rec_off = nullptr;
     uint64_t* d_key = nullptr;
@@ -177,7 +179,7 @@ extern "C" const char* sbr_last_error(const sbr_ctx* ctx) { return ctx ? ctx->er
 
 static void free_slot(Slot& s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
-    cudaFree(s.d_text); cudaFree(s.d_hdr); cudaFree(s.d_desc); cudaFree(s.d_rec_off); cudaFree(s.d_key);
+    cudaFree(s.d_text); cudaFree(s.d_hdr2); cudaFree(s.d_desc); cudaFree(s.d_rec_off); cudaFree(s.d_key);
     cudaFree(s.d_done); cudaFree(s.d_info); cudaFree(s.d_region_base); cudaFree(s.d_seg_rec_off); cudaFree(s.d_seg_key);
     cudaFree(s.d_assign); cudaFree(s.d_cta_cnt); cudaFree(s.d_bin_count); cudaFree(s.d_bin_start); cudaFree(s.d_order);
     cudaFreeHost(s.h_text); cudaFreeHost(s.h_hdr); cudaFreeHost(s.h_rec_off); cudaFreeHost(s.h_key);
@@ -292,7 +294,9 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
     for (auto& s : c->slots) {
         CU(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CU(c, cudaEventCreateWithFlags(&s.hdr_ready, cudaEventDisableTiming));
-        CU(c, cudaMalloc(&s.d_hdr, sizeof(BatchHeader)));
+        CU(c, cudaMalloc(&s.d_hdr2, 2 * sizeof(BatchHeader)));
+        CU(c, cudaMemset(s.d_hdr2, 0, 2 * sizeof(BatchHeader)));
+        s.d_hdr = s.d_hdr2;
         CU(c, cudaMalloc(&s.d_desc, (size_t)c->max_tiles * sizeof(uint4)));
         CU(c, cudaMalloc(&s.d_rec_off, (mr + 1) * sizeof(uint32_t)));
         CU(c, cudaMalloc(&s.d_key, (mr + 4) * sizeof(uint64_t)));
@@ -377,11 +381,12 @@ static int launch_match_partition(sbr_ctx* c, Slot& s, const uint8_t* d_text, ui
     L.grid = c->plan.grid;
     L.fused = c->fused ? 1 : 0; L.nbits = c->plan.nbits;
     L.bin_count = s.d_bin_count; L.bin_start = s.d_bin_start; L.order = s.d_order;
+    L.zero_next = s.d_hdr2 + (s.hdr_idx ^ 1u);
     CU(c, match_launch(L, st));
     if (ev) CU(c, cudaEventRecord(ev[2], st));
     if (!c->fused)
         CU(c, partition_launch(s.d_assign, s.d_hdr, c->nbins, s.d_cta_cnt, s.d_bin_count, s.d_bin_start, s.d_order,
-                               s.d_done, c->plan, st));
+                               s.d_done, s.d_hdr2 + (s.hdr_idx ^ 1u), c->plan, st));
     if (ev) CU(c, cudaEventRecord(ev[3], st));
     c->launches += 1 + (c->fused ? 0 : 2);
     return SBR_OK;
@@ -395,7 +400,9 @@ static int launch_pipeline(sbr_ctx* c, Slot& s, const uint8_t* d_text, uint32_t 
                            cudaStream_t st) {
     cudaEvent_t* ev = nullptr;
     if (c->timing && c->ev_used < TIMING_RING) ev = &c->ev[(size_t)c->ev_used++ * 4];
-    CU(c, cudaMemsetAsync(s.d_hdr, 0, sizeof(BatchHeader), st));
+    // the header: the slot's two alternate; this batch takes the one the previous batch's last kernel cleared
+    s.hdr_idx ^= 1u;
+    s.d_hdr = s.d_hdr2 + s.hdr_idx;
     s.cur_text = d_text;
     s.cur_cap_r = 0;
     if (ev) CU(c, cudaEventRecord(ev[0], st));

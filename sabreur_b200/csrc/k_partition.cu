@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_scatter(const uint16_t* __rest
                                                           const BatchHeader* __restrict__ hdr, uint32_t nbins, uint32_t nbits,
                                                           const uint32_t* __restrict__ cta_cnt /* scanned over CTAs */,
                                                           const uint32_t* __restrict__ bin_start,
-                                                          uint32_t* __restrict__ order) {
+                                                          uint32_t* __restrict__ order, BatchHeader* zero_next) {
     extern __shared__ uint32_t s_cur[];  // [PART_WARPS][nbins]: counts first, then the running cursor per bin
     const uint32_t n = hdr->n_records;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -143,6 +143,8 @@ __global__ void __launch_bounds__(PART_THREADS) k_scatter(const uint16_t* __rest
         }
     }
     __syncthreads();
+    // the slot's other header is cleared here for the next batch (saves a memset per batch)
+    if (blockIdx.x == 0 && threadIdx.x < sizeof(BatchHeader) / 4 && zero_next) reinterpret_cast<uint32_t*>(zero_next)[threadIdx.x] = 0u;
     if (lo >= hi) return;  // warp-uniform
     const uint32_t lt = (1u << lane) - 1u;
     constexpr int U = 4;  // the loads of four 32-record groups are in flight together; ranking stays in order
@@ -201,9 +203,9 @@ cudaError_t partition_prepare() {
 
 cudaError_t partition_launch(const uint16_t* d_assign, const BatchHeader* d_hdr, uint32_t nbins,
                              uint32_t* d_cta_cnt, uint32_t* d_bin_count, uint32_t* d_bin_start, uint32_t* d_order,
-                             uint32_t* d_done_counter, const PartitionPlan& p, cudaStream_t stream) {
+                             uint32_t* d_done_counter, BatchHeader* d_zero_next, const PartitionPlan& p, cudaStream_t stream) {
     k_binscan<<<nbins, PART_THREADS, 0, stream>>>(d_cta_cnt, (uint32_t)p.grid, nbins, d_bin_count, d_bin_start, d_done_counter);
-    k_scatter<<<p.grid, PART_THREADS, p.smem, stream>>>(d_assign, d_hdr, nbins, p.nbits, d_cta_cnt, d_bin_start, d_order);
+    k_scatter<<<p.grid, PART_THREADS, p.smem, stream>>>(d_assign, d_hdr, nbins, p.nbits, d_cta_cnt, d_bin_start, d_order, d_zero_next);
     return cudaGetLastError();
 }
 

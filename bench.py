@@ -372,7 +372,7 @@ def main():
         probe_n = 200_000
         probe = texts[0][: probe_n * rec].cpu().numpy()
         s1, _, _ = cpu_reference(w, tab, probe, rec, 1)
-        n = int(max(probe_n, min(units, 8_000_000, s1 * args.cpu_seconds)))
+        n = int(max(probe_n, min(units, 16_000_000, s1 * args.cpu_seconds)))
         sample = texts[0][: n * rec].cpu().numpy()
         threads = os.cpu_count() or 1
         single, dt1, allc = cpu_reference(w, tab, sample, rec, threads)

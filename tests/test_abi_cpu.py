@@ -70,3 +70,17 @@ def test_synth_table_and_host_generator(lib):
     b = synth.reads_host(w, tab, 20, 10)
     assert (a[20 * w.rec_bytes:30 * w.rec_bytes] == b).all()
     assert w.rec_bytes == 321 and synth.CFG5.rec_bytes == 266
+
+
+def test_plain_c_caller_compiles_and_links(lib, tmp_path):
+    """include/sabreur_gpu.h is C99 and a plain C program links against the library (no C++/torch types in the ABI)"""
+    import subprocess
+    from sabreur_b200 import _ffi
+    hdr = os.path.join(ROOT, "include", "sabreur_gpu.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-x", "c", hdr])
+    exe = os.path.join(ROOT, "sabreur_b200", "bin", "abi_smoke")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    libdir = os.path.dirname(_ffi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-o", exe, os.path.join(ROOT, "tests", "abi_smoke.c"),
+                           "-L" + libdir, "-lsabreur_gpu", "-Wl,-rpath," + libdir])
+    assert os.path.exists(exe)

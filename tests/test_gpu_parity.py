@@ -410,3 +410,20 @@ def test_fastq_many_odd_records(gpu):
         nl = b"\r\n" if odd and rng.random() < 0.5 else b"\n"
         out += b"@q%d" % i + nl + s + nl + ((b"+q%d" % i) if odd else b"+") + nl + q + nl
     _check_against_oracle(gpu, bytes(out), bcs, 2, batch_bytes=8 << 20, chunk=1 << 20)
+
+
+def test_plain_c_caller(gpu):
+    """tests/abi_smoke.c: a C99 program over the C ABI (built by the CPU test or here)"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "sabreur_b200", "bin", "abi_smoke")
+    libdir = os.path.join(root, "sabreur_b200", "lib")
+    if not os.path.exists(exe):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        subprocess.check_call(["gcc", "-std=c99", "-o", exe, os.path.join(root, "tests", "abi_smoke.c"), "-L" + libdir,
+                               "-lsabreur_gpu", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    # r1 ACGT exact, r2 ACGA one mismatch -> row 0; r3 TTTT -> unknown; r4 GGGG -> row 1
+    assert out.stdout.strip() == "ok 4 2 1 1 | 0 0 2 1"

@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_scan_fast(FastArgs A) {
     const uint32_t wl_addr = smem_u32(wl + GHOSTS);  // shared-window address of the slice's entry 0
 
     const uint64_t text_policy = l2_evict_first_policy();
+    const uint64_t keep_policy = l2_evict_last_policy();  // the per-record output: the match kernel reads it next
     auto issue = [&](int s, uint32_t tile) {  // thread 0 only
         uint32_t lo = tile * (uint32_t)FAST_TILE;
         uint32_t valid = min((uint32_t)FAST_TILE, A.nbytes - lo);
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_scan_fast(FastArgs A) {
             // single-buffered: the load of the NEXT tile can only start when this one has been scanned, so at least
             // bring it into L2 now (the region's last tile prefetches the one a FASTQ region runs over into)
             const uint32_t nlo = lo + (uint32_t)FAST_TILE;
-            bulk_prefetch_l2(A.text + nlo, (min((uint32_t)FAST_TILE, A.nbytes - nlo) + 15u) & ~15u);
+            bulk_prefetch_l2(A.text + nlo, (min((uint32_t)FAST_TILE, A.nbytes - nlo) + 15u) & ~15u, text_policy);
         }
     };
 
@@ -540,8 +541,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_scan_fast(FastArgs A) {
                         const uint32_t rl = (L - fo) >> 2;
                         if (bits || rl >= A.cap_r) S.fail = 1;
                         else {
-                            seg_off_c[rl] = start;
-                            seg_key_c[rl] = key;
+                            st_keep_u32(seg_off_c + rl, start, keep_policy);
+                            st_keep_u64(seg_key_c + rl, key, keep_policy);
                             // records are committed in ascending order: the last one of the slice (or the one that
                             // closes the region) carries the slice's maxima to the CTA
                             const bool closes = p3 + 1 >= region_hi;
@@ -592,8 +593,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_scan_fast(FastArgs A) {
                     // a prefix cut by the end of a non-final batch belongs to the incomplete last record: no error
                     if (rl >= A.cap_r || why == 1 || (why == 2 && A.final_batch)) S.fail = 1;
                     else {
-                        seg_off_c[rl] = p + 1;
-                        seg_key_c[rl] = key;
+                        st_keep_u32(seg_off_c + rl, p + 1, keep_policy);
+                        st_keep_u64(seg_key_c + rl, key, keep_policy);
                     }
                     if (u == nr_w - 1)  // ascending over the tiles: a plain store per warp, the maximum is taken at the end
                         S.wlast[warp] = ((unsigned long long)(base + pre_n + idx + 1) << 32) | (unsigned long long)(p + 1);

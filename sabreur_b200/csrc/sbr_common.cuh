@@ -126,8 +126,21 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32
 }
 
 // bulk prefetch global -> L2 (no shared memory involved): the tile after next is on its way while this one is scanned
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(policy) : "memory");
+}
+
+// stores that should stay in L2 until the next kernel has read them (the scan's per-record output, read by the match kernel)
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_keep_u32(uint32_t* p, uint32_t v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void st_keep_u64(uint64_t* p, uint64_t v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(policy) : "memory");
 }
 
 // single-copy-atomic 128-bit accesses for the look-back descriptors (SASS LDG/STG.E.128.STRONG.GPU)

@@ -206,3 +206,29 @@ def test_duplicate_barcode_rows_keep_the_last_rows_file(tmp_path):
     _run([str(tsv), str(p), "-o", "out"], tmp_path)
     assert os.path.getsize(tmp_path / "out" / "first.fq") == 0
     assert open(tmp_path / "out" / "second.fq", "rb").read() == b"@a\nACGTAA\n+\nIIIIII\n"
+
+
+def test_tiny_and_empty_inputs(tmp_path):
+    tsv = tmp_path / "bc.tsv"
+    tsv.write_text("ACGT\tx.out\n")
+    # one FASTQ record, no final newline: needletail accepts it; the output gets the canonical newline
+    p = tmp_path / "one.fq"
+    p.write_bytes(b"@only\nACGTTT\n+\nIIIIII")
+    _run([str(tsv), str(p), "-o", "o1"], tmp_path)
+    assert open(tmp_path / "o1" / "x.out", "rb").read() == b"@only\nACGTTT\n+\nIIIIII\n"
+    assert not os.path.exists(tmp_path / "o1" / "unknown.fa")
+    # one FASTA record over several lines
+    p = tmp_path / "one.fa"
+    p.write_bytes(b">only desc\nAC\nGT\nTT\n")
+    _run([str(tsv), str(p), "-o", "o2"], tmp_path)
+    assert open(tmp_path / "o2" / "x.out", "rb").read() == b">only desc\nACGTTT\n"
+    # a file that is neither FASTA nor FASTQ: the parser refuses it (exit 1), the outputs exist and are empty
+    p = tmp_path / "junk.txt"
+    p.write_bytes(b"hello world\n")
+    r = _run([str(tsv), str(p), "-o", "o3"], tmp_path, ok=False)
+    assert r.returncode == 1 and os.path.getsize(tmp_path / "o3" / "x.out") == 0
+    # five bytes is niffler's minimum
+    p = tmp_path / "short.fq"
+    p.write_bytes(b"@a\n")
+    r = _run([str(tsv), str(p), "-o", "o4"], tmp_path, ok=False)
+    assert r.returncode == 1 and "too short" in r.stderr

@@ -187,6 +187,29 @@ def run_reference(args, w, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_near_gpu(local_rank: int):
+    """Best effort: run this rank on the CPUs of its GPU's NUMA node, so that the pinned slot buffers (first touch) and
+    the copies stay on the local socket.  Returns a short description for the JSON line."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return {"gpu": bdf, "numa_node": None}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use:
+            os.sched_setaffinity(0, use)
+        return {"gpu": bdf, "numa_node": node, "cpus_bound": len(use), "cpus_allowed": len(allowed)}
+    except Exception as e:  # no sysfs, no permission ...: run unbound
+        return {"error": str(e)[:80]}
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -210,6 +233,7 @@ def main():
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
+    numa = bind_near_gpu(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -359,7 +383,8 @@ def main():
         barrier()
         e2e_units = n_e2e * eb / len(mates)
         e2e = {"value": world * e2e_units * e2e_steps / dt, "unit": "pairs/s" if w.paired else "reads/s",
-               "h2d_bytes_per_step": n_e2e * eb * rec, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+               "h2d_bytes_per_step": world * n_e2e * eb * rec, "d2h_bytes_per_step": world * d2h, "steps": e2e_steps,
+               "host_placement_rank0": numa,
                "ms_per_step": 1e3 * dt / e2e_steps, "batch_bytes": eb * rec, "slots": S,
                "how": "pinned host text -> sbr_submit (H2D, scan, match, partition) -> sbr_wait (D2H rec_off, assign, order)"}
         dm2.close()

@@ -371,10 +371,19 @@ private:
             flight.pop_front();
             wait(b);
             const bool errored = (b.res.status_flags & SBR_ST_ERROR_MASK) != 0;
-            if (!errored && b.res.consumed < b.n) {
+            bool blank_tail = false;
+            if (!errored && b.res.consumed < b.n && b.final_batch && !(b.res.status_flags & SBR_ST_REC_OVERFLOW)) {
+                // end of the stream: what the library leaves behind without an error are the blank lines needletail
+                // tolerates after the last record (sbr_submit drops up to three of them)
+                const uint8_t* buf = gpus_[b.gpu].slot_host[b.slot];
+                blank_tail = true;
+                // (sbr_submit pads the text it copies with zero bytes: the first 16 bytes of the dropped tail may read 0)
+                for (uint64_t q = b.off + b.res.consumed; q < b.off + b.n; ++q)
+                    blank_tail = blank_tail && (buf[q] == '\n' || buf[q] == '\r' || buf[q] == 0);
+                if (!blank_tail) throw std::runtime_error("internal: final batch left bytes unconsumed without an error");
+            }
+            if (!errored && b.res.consumed < b.n && !blank_tail) {
                 // the guess was wrong (or the record capacity was hit): the rest belongs in front of the next batch
-                if (b.final_batch && !(b.res.status_flags & SBR_ST_REC_OVERFLOW))
-                    throw std::runtime_error("internal: final batch left bytes unconsumed without an error");
                 const uint8_t* buf = gpus_[b.gpu].slot_host[b.slot];
                 prefix_.assign(buf + b.off + b.res.consumed, buf + b.off + b.n);
                 if (b.res.consumed == 0) throw std::runtime_error("no progress: a single record is larger than a batch");
@@ -425,8 +434,8 @@ private:
             b.final_batch = true;
             submit(b);
             wait(b);
-            if (!(b.res.status_flags & SBR_ST_ERROR_MASK) && b.res.consumed < b.n) {
-                prefix_.assign(buf + b.off + b.res.consumed, buf + b.off + b.n);
+            if (!(b.res.status_flags & SBR_ST_ERROR_MASK) && b.res.consumed < b.n && (b.res.status_flags & SBR_ST_REC_OVERFLOW)) {
+                prefix_.assign(buf + b.off + b.res.consumed, buf + b.off + b.n);  // (else: the stream's blank tail)
                 extra_.seq = b.seq + 1;
             }
             if (stats_) { ++stats_->batches; stats_->records += b.res.n_records; }

@@ -175,6 +175,20 @@ def test_noncanonical_input_is_reserialised(tmp_path):
     assert not os.path.exists(tmp_path / "out" / "unknown.fa") or open(tmp_path / "out" / "unknown.fa", "rb").read() == outs[-1]
 
 
+@pytest.mark.parametrize("tail", [b"\n", b"\n\n\n", b"\r\n"])
+def test_blank_lines_after_the_last_record_are_tolerated(tmp_path, tail):
+    """needletail accepts a few blank lines at the end of a FASTQ stream: not an error, nothing written for them"""
+    text = b"".join(b"@r%d\nACGTAAGG\n+\nIIIIIIII\n" % i for i in range(50)) + tail
+    p = tmp_path / "in.fq"
+    p.write_bytes(text)
+    tsv = tmp_path / "bc.tsv"
+    tsv.write_text("ACGT\tx.fq\n")
+    _run([str(tsv), str(p), "-o", "out"], tmp_path)
+    outs = orc.demux_outputs(text, [b"ACGT"], 0)
+    assert open(tmp_path / "out" / "x.fq", "rb").read() == outs[0] and len(outs[0]) == len(text) - len(tail)
+    assert not os.path.exists(tmp_path / "out" / "unknown.fa")
+
+
 def test_se_parse_error_exits_1_after_writing_the_good_records(tmp_path):
     good = b"@a\nACGTAA\n+\nIIIIII\n@b\nCCGTAA\n+\nIIIIII\n"
     bad = good + b"@c\nACGTAA\n-\nIIIIII\n@d\nACGTAA\n+\nIIIIII\n"

@@ -1,0 +1,163 @@
+"""Randomised end-to-end hunt on the GPU box: the `sabreur` command line (C++ host over the C ABI) on the random cases of
+tools/fuzz_gpu.py -- plain / gzip / multi-member gzip input, every output format, 1 MiB batches (guessed cuts, tails,
+re-submissions), single- and paired-end -- every output file (decompressed) against the oracle's per-barcode bytes.
+Test infrastructure (the oracle is the checker).
+
+    python tools/fuzz_cli.py [--seconds 120] [--seed 1] [--out gpurun_out/fuzz_cli]"""
+from __future__ import annotations
+
+import argparse
+import bz2
+import gzip
+import json
+import lzma
+import os
+import random
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import fuzz_gpu as fz  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+SABREUR = os.path.join(ROOT, "sabreur_b200", "bin", "sabreur")
+SELFTEST = os.path.join(ROOT, "sabreur_b200", "bin", "codec_selftest")
+
+
+def plain(path: str) -> bytes:
+    data = open(path, "rb").read()
+    if not data:
+        return b""
+    if data[:2] == b"\x1f\x8b":
+        return gzip.decompress(data)
+    if data[:3] == b"BZh":
+        return bz2.decompress(data)
+    if data[:6] == b"\xfd7zXZ\x00":
+        return lzma.decompress(data)
+    if data[:4] == b"\x28\xb5\x2f\xfd":
+        return subprocess.run([SELFTEST, "cat", path], capture_output=True, check=True).stdout
+    return data
+
+
+def write_input(rng: random.Random, path: str, text: bytes) -> str:
+    how = rng.choice(("plain", "plain", "gz", "gz_members"))
+    if how == "plain":
+        open(path, "wb").write(text)
+        return path
+    path += ".gz"
+    with open(path, "wb") as f:
+        if how == "gz":
+            f.write(gzip.compress(text, 1))
+        else:  # several members, cut at arbitrary bytes (bgzip-like)
+            cuts = sorted(rng.randrange(len(text) + 1) for _ in range(rng.randint(1, 6)))
+            for a, b in zip([0] + cuts, cuts + [len(text)]):
+                f.write(gzip.compress(text[a:b], 1))
+    return path
+
+
+def run_case(seed: int, workdir: str):
+    rng = random.Random(seed ^ 0xC11)
+    text, bcs, m, _batch, _chunk, _uf, params, starts = fz.make_case(seed)
+    if params["inject"] or len(text) > 6_000_000:
+        return None, params
+    uniq = []
+    for b in bcs:  # (a repeated row never wins under first-match; the TSV keeps one file per barcode)
+        if b not in uniq:
+            uniq.append(b)
+    bcs = uniq
+    paired = rng.random() < 0.3
+    texts = [text]
+    if paired:  # the mates are independent streams: the reverse file is the forward one with its records reversed
+        recs = [text[a:b] for a, b in zip(starts, starts[1:] + [len(text)])]
+        texts.append(b"".join(reversed(recs)) if params["tail"] == "nl" else text)
+    d = tempfile.mkdtemp(dir=workdir)
+    try:
+        ext = ".fq" if params["fastq"] else ".fa"
+        paths = [write_input(rng, os.path.join(d, f"in_R{i + 1}{ext}"), t) for i, t in enumerate(texts)]
+        tsv = os.path.join(d, "bc.tsv")
+        with open(tsv, "w") as f:
+            for i, b in enumerate(bcs):
+                f.write(f"{b.decode()}\tb{i}_R1{ext}" + (f"\tb{i}_R2{ext}" if paired else "") + "\n")
+        fmt = rng.choice((None, None, "gz", "zst", "bz2", "xz"))
+        # (the host keeps 1/8 of a batch free for carried-over bytes: a record must fit in there)
+        batch_mb = rng.choice((4, 8, 256)) if params["shape"] in ("long", "mixed") else rng.choice((1, 1, 2, 256))
+        args = [SABREUR, tsv] + paths + ["-o", "out", "-m", str(m), "--batch-mb", str(batch_mb), "-q"]
+        if fmt:
+            args += ["-f", fmt, "-l", str(rng.randint(1, 4))]
+        if paired and rng.random() < 0.3:
+            args.append("--sequential-mates")
+        params.update(paired=paired, out_fmt=fmt, inputs=[os.path.basename(p) for p in paths], n_bc=len(bcs))
+        r = subprocess.run(args, capture_output=True, text=True, cwd=d, timeout=300)
+        if r.returncode != 0:
+            return f"exit {r.returncode}: {r.stderr[-400:]}", params
+        out = os.path.join(d, "out")
+        files = {}
+        for name in os.listdir(out):
+            stem = name
+            for e in (".gz", ".zst", ".bz2", ".xz"):
+                if stem.endswith(e):
+                    stem = stem[:-len(e)]
+            files[stem] = os.path.join(out, name)
+        for mate, t in enumerate(texts):
+            exp = orc.demux_outputs(t, bcs, m)
+            for i in range(len(bcs)):
+                stem = f"b{i}_R{mate + 1}{ext}"
+                if stem not in files:
+                    return f"missing {stem}", params
+                if plain(files[stem]) != exp[i]:
+                    return f"{stem} differs from the oracle's bytes", params
+            unk = ("unknown_R%d.fa" % (mate + 1)) if paired else "unknown.fa"
+            got = plain(files[unk]) if unk in files else b""
+            if got != exp[-1]:
+                return f"{unk} differs from the oracle's bytes", params
+            if unk in files and not exp[-1]:
+                return f"{unk} exists but should have been deleted", params
+        return "", params
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=120.0)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--out", default="gpurun_out/fuzz_cli")
+    a = ap.parse_args()
+    os.makedirs(a.out, exist_ok=True)
+    if not os.path.exists(SABREUR):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "sabreur_b200", "csrc", "host")])
+    work = tempfile.mkdtemp(prefix="fuzzcli")
+    t0 = time.time()
+    n = ran = fails = 0
+    while time.time() - t0 < a.seconds:
+        seed = a.seed * 7_000_003 + n
+        n += 1
+        try:
+            why, params = run_case(seed, work)
+        except Exception as e:  # noqa: BLE001
+            why, params = f"exception: {e!r}", dict(seed=seed)
+        if why is None:
+            continue
+        ran += 1
+        if why:
+            fails += 1
+            params["why"] = why
+            print("FAIL", json.dumps(params)[:700], flush=True)
+            with open(os.path.join(a.out, f"case_{seed}.json"), "w") as f:
+                json.dump(params, f)
+            if fails >= 5:
+                break
+    shutil.rmtree(work, ignore_errors=True)
+    print(f"fuzz_cli: {ran} cases, {fails} failures, {time.time() - t0:.0f} s", flush=True)
+    with open(os.path.join(a.out, "summary.json"), "w") as f:
+        json.dump(dict(cases=ran, failures=fails, seconds=time.time() - t0, seed=a.seed), f)
+    sys.exit(1 if fails else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -9,6 +9,9 @@
 //   writer thread   takes results in batch order, gathers every bin's records (order[] / rec_off[]) into one
 //                   buffer per output file, compresses it as one member and appends it: files keep input order
 //                   exactly like the sequential reference (src/demux.rs:49-66, utils.rs:133-158).
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include "demux_host.hpp"
 
 #include <algorithm>
@@ -127,6 +130,30 @@ uint64_t guess_cut(const uint8_t* p, uint64_t n, uint32_t fmt, uint64_t window) 
     for (size_t j = 2; j < starts.size(); ++j)  // starts[j-2] is two lines after starts[j]
         if (p[starts[j]] == '@' && p[starts[j - 2]] == '+') return starts[j];
     return n;
+}
+
+// newlines in [p, p + n): 64 bytes per step with byte-wide counters (SSE2 is part of x86-64), ~30 GB/s per core
+static uint64_t count_newlines(const uint8_t* p, uint64_t n) {
+    uint64_t c = 0, i = 0;
+#if defined(__x86_64__)
+    const __m128i nl = _mm_set1_epi8('\n'), zero = _mm_setzero_si128();
+    while (n - i >= 64) {
+        uint64_t blocks = (n - i) / 64;
+        if (blocks > 255) blocks = 255;  // byte counters: at most 255 increments before they are folded
+        __m128i a0 = zero, a1 = zero, a2 = zero, a3 = zero;
+        for (uint64_t b = 0; b < blocks; ++b, i += 64) {
+            a0 = _mm_sub_epi8(a0, _mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(p + i)), nl));
+            a1 = _mm_sub_epi8(a1, _mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(p + i + 16)), nl));
+            a2 = _mm_sub_epi8(a2, _mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(p + i + 32)), nl));
+            a3 = _mm_sub_epi8(a3, _mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(p + i + 48)), nl));
+        }
+        const __m128i t = _mm_add_epi64(_mm_add_epi64(_mm_sad_epu8(a0, zero), _mm_sad_epu8(a1, zero)),
+                                        _mm_add_epi64(_mm_sad_epu8(a2, zero), _mm_sad_epu8(a3, zero)));
+        c += (uint64_t)_mm_cvtsi128_si64(t) + (uint64_t)_mm_cvtsi128_si64(_mm_unpackhi_epi64(t, t));
+    }
+#endif
+    for (; i < n; ++i) c += p[i] == '\n';
+    return c;
 }
 
 // canonical bytes of one record (needletail write_fasta / write_fastq, LineEnding::Unix; src/utils.rs:142-154)
@@ -289,27 +316,44 @@ private:
                 if (carry.size() > reserve_) throw std::runtime_error("a single record is larger than the batch reserve");
                 b.off = reserve_ - carry.size();
                 std::memcpy(buf + b.off, carry.data(), carry.size());
+                // A batch holds at most max_records records (the library's default: batch_bytes / 32 + 16).  A FASTQ
+                // record has four newlines and a FASTA record at least two, so filling stops once the newlines that
+                // many records could own are in: streams of very short records (< 32 bytes) become smaller batches
+                // instead of overflowing the record capacity.
+                const uint64_t max_records = cap_ / 32 + 16;
+                uint64_t nl_seen = count_newlines(carry.data(), carry.size());
+                const uint64_t step = std::max<uint64_t>(64 << 10, std::min<uint64_t>(reserve_ / 2, 4ull << 20));
+                std::vector<uint8_t> spill;  // read, but behind the newline budget: goes to the next batch
                 uint64_t fill = reserve_;
                 while (fill < cap_) {
-                    size_t got = in.read(buf + fill, cap_ - fill);
+                    size_t got = in.read(buf + fill, std::min<uint64_t>(step, cap_ - fill));
                     if (got == 0) { eof = true; break; }
+                    if (fmt == 0) fmt = buf[b.off] == '>' ? SBR_FMT_FASTA : SBR_FMT_FASTQ;
+                    const uint64_t budget = (max_records - 64) * (fmt == SBR_FMT_FASTA ? 2 : 4);
+                    const uint64_t c = count_newlines(buf + fill, got);
+                    if (nl_seen + c > budget) {
+                        uint64_t keep = 0, left = budget > nl_seen ? budget - nl_seen : 0;
+                        while (keep < got && left) left -= buf[fill + keep++] == '\n';
+                        spill.assign(buf + fill + keep, buf + fill + got);
+                        fill += keep;
+                        break;
+                    }
+                    nl_seen += c;
                     fill += got;
                 }
-                if (!eof) {  // learn about the end of the stream before deciding whether this batch is final
+                if (!eof && spill.empty()) {  // learn about the end of the stream before deciding whether this batch is final
                     uint8_t probe;
                     if (in.read(&probe, 1) == 0) eof = true;
                     else { peeked_ = true; peek_byte_ = probe; }
                 }
                 uint64_t n = fill - b.off;
-                if (seq == 0) {
-                    if (n == 0) { bad_flags_ = SBR_ST_INVALID_START; bad_record_ = 0; break; }  // empty input: needletail refuses it
-                    fmt = buf[b.off] == '>' ? SBR_FMT_FASTA : SBR_FMT_FASTQ;
-                }
+                if (seq == 0 && n == 0) { bad_flags_ = SBR_ST_INVALID_START; bad_record_ = 0; break; }  // empty input: needletail refuses it
                 carry.clear();
                 if (!eof) {
-                    uint64_t cut = guess_cut(buf + b.off, n, fmt, std::min<uint64_t>(reserve_, 1ull << 20));
+                    uint64_t cut = guess_cut(buf + b.off, n, fmt, std::min<uint64_t>(spill.empty() ? reserve_ : reserve_ / 2, 1ull << 20));
                     if (cut == 0) cut = n;  // no boundary in sight: let the scan decide
                     carry.assign(buf + b.off + cut, buf + b.off + n);
+                    carry.insert(carry.end(), spill.begin(), spill.end());
                     if (peeked_) { carry.push_back(peek_byte_); peeked_ = false; }
                     // FASTA: a line that starts with '>' IS a record start (no guess involved), so the batch in front
                     // of it is submitted as "ends at a record boundary"; a non-final FASTA batch would otherwise hold

@@ -189,6 +189,30 @@ def test_blank_lines_after_the_last_record_are_tolerated(tmp_path, tail):
     assert not os.path.exists(tmp_path / "out" / "unknown.fa")
 
 
+@pytest.mark.parametrize("fastq", [False, True])
+def test_streams_of_very_short_records_do_not_overflow_the_record_capacity(tmp_path, fastq):
+    """records of < 32 bytes: more of them fit in a batch than its record capacity (batch_bytes / 32); the reader fills
+    batches by a newline budget, so nothing overflows and every record is written once"""
+    import random
+    rng = random.Random(5)
+    recs = []
+    for i in range(150_000):
+        s = bytes(rng.choices(b"ACGT", k=rng.randint(4, 6)))
+        recs.append(b"@%x\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n" if fastq else b">%x\n" % i + s + b"\n")
+    text = b"".join(recs)
+    assert len(text) / len(recs) < 32
+    p = tmp_path / ("in.fq" if fastq else "in.fa")
+    p.write_bytes(text)
+    bcs = [b"ACGT", b"CCGT", b"TTGA"]
+    tsv = tmp_path / "bc.tsv"
+    tsv.write_text("".join(f"{b.decode()}\to{i}.fx\n" for i, b in enumerate(bcs)))
+    _run([str(tsv), str(p), "-o", "out", "-m", 1, "--batch-mb", 1], tmp_path)
+    outs = orc.demux_outputs(text, bcs, 1)
+    for i in range(3):
+        assert open(tmp_path / "out" / f"o{i}.fx", "rb").read() == outs[i]
+    assert open(tmp_path / "out" / "unknown.fa", "rb").read() == outs[-1]
+
+
 def test_se_parse_error_exits_1_after_writing_the_good_records(tmp_path):
     good = b"@a\nACGTAA\n+\nIIIIII\n@b\nCCGTAA\n+\nIIIIII\n"
     bad = good + b"@c\nACGTAA\n-\nIIIIII\n@d\nACGTAA\n+\nIIIIII\n"

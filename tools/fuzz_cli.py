@@ -63,8 +63,17 @@ def write_input(rng: random.Random, path: str, text: bytes) -> str:
 def run_case(seed: int, workdir: str):
     rng = random.Random(seed ^ 0xC11)
     text, bcs, m, _batch, _chunk, _uf, params, starts = fz.make_case(seed)
-    if params["inject"] or len(text) > 6_000_000:
+    if len(text) > 6_000_000:
         return None, params
+    err = None
+    good = text
+    if params["inject"]:  # a violation: the records in front of it are still written (demux.rs:50 / 101, 114)
+        try:
+            orc.demux(text, bcs, m)
+            return "oracle accepted the damaged input (generator bug)", params
+        except orc.OracleError as e:
+            err = e
+        good = text[:starts[err.record]] if err.record < len(starts) else text
     uniq = []
     for b in bcs:  # (a repeated row never wins under first-match; the TSV keeps one file per barcode)
         if b not in uniq:
@@ -72,9 +81,11 @@ def run_case(seed: int, workdir: str):
     bcs = uniq
     paired = rng.random() < 0.3
     texts = [text]
+    goods = [good]
     if paired:  # the mates are independent streams: the reverse file is the forward one with its records reversed
         recs = [text[a:b] for a, b in zip(starts, starts[1:] + [len(text)])]
-        texts.append(b"".join(reversed(recs)) if params["tail"] == "nl" else text)
+        texts.append(b"".join(reversed(recs)) if params["tail"] == "nl" and not err else text)
+        goods.append(texts[1] if not err else good)
     d = tempfile.mkdtemp(dir=workdir)
     try:
         ext = ".fq" if params["fastq"] else ".fa"
@@ -93,8 +104,12 @@ def run_case(seed: int, workdir: str):
             args.append("--sequential-mates")
         params.update(paired=paired, out_fmt=fmt, inputs=[os.path.basename(p) for p in paths], n_bc=len(bcs))
         r = subprocess.run(args, capture_output=True, text=True, cwd=d, timeout=300)
-        if r.returncode != 0:
-            return f"exit {r.returncode}: {r.stderr[-400:]}", params
+        # SE: `record?` surfaces the parse error (exit 1); PE: `while let Some(Ok(..))` just stops that mate; a read
+        # shorter than the barcode is the slice panic (exit 101) in both
+        want_rc = 0 if not err else (101 if err.code == orc.E_SHORT_READ else (0 if paired else 1))
+        params["want_rc"] = want_rc
+        if r.returncode != want_rc:
+            return f"exit {r.returncode}, expected {want_rc}: {r.stderr[-400:]}", params
         out = os.path.join(d, "out")
         files = {}
         for name in os.listdir(out):
@@ -103,8 +118,10 @@ def run_case(seed: int, workdir: str):
                 if stem.endswith(e):
                     stem = stem[:-len(e)]
             files[stem] = os.path.join(out, name)
-        for mate, t in enumerate(texts):
-            exp = orc.demux_outputs(t, bcs, m)
+        for mate, t in enumerate(goods):
+            if want_rc == 101 and paired and mate == 1:
+                break  # the forward pass panicked: the reverse pass never ran (or was cut short)
+            exp = orc.demux_outputs(t, bcs, m) if t else [b""] * (len(bcs) + 1)
             for i in range(len(bcs)):
                 stem = f"b{i}_R{mate + 1}{ext}"
                 if stem not in files:
@@ -115,7 +132,7 @@ def run_case(seed: int, workdir: str):
             got = plain(files[unk]) if unk in files else b""
             if got != exp[-1]:
                 return f"{unk} differs from the oracle's bytes", params
-            if unk in files and not exp[-1]:
+            if unk in files and not exp[-1] and r.returncode == 0:
                 return f"{unk} exists but should have been deleted", params
         return "", params
     finally:

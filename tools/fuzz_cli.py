@@ -102,6 +102,7 @@ def run_case(seed: int, workdir: str):
             args += ["-f", fmt, "-l", str(rng.randint(1, 4))]
         if paired and rng.random() < 0.3:
             args.append("--sequential-mates")
+        args += os.environ.get("SABREUR_EXTRA_ARGS", "").split()  # e.g. "--gpus 2" on a multi-GPU box
         params.update(paired=paired, out_fmt=fmt, inputs=[os.path.basename(p) for p in paths], n_bc=len(bcs))
         r = subprocess.run(args, capture_output=True, text=True, cwd=d, timeout=300)
         # SE: `record?` surfaces the parse error (exit 1); PE: `while let Some(Ok(..))` just stops that mate; a read

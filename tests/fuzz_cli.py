@@ -1,9 +1,9 @@
 """Randomised end-to-end hunt on the GPU box: the `sabreur` command line (C++ host over the C ABI) on the random cases of
-tools/fuzz_gpu.py -- plain / gzip / multi-member gzip input, every output format, 1 MiB batches (guessed cuts, tails,
+tests/fuzz_gpu.py -- plain / gzip / multi-member gzip input, every output format, 1 MiB batches (guessed cuts, tails,
 re-submissions), single- and paired-end -- every output file (decompressed) against the oracle's per-barcode bytes.
 Test infrastructure (the oracle is the checker).
 
-    python tools/fuzz_cli.py [--seconds 120] [--seed 1] [--out gpurun_out/fuzz_cli]"""
+    python tests/fuzz_cli.py [--seconds 120] [--seed 1] [--out gpurun_out/fuzz_cli]"""
 from __future__ import annotations
 
 import argparse
@@ -21,7 +21,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import fuzz_gpu as fz  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 

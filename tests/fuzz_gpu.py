@@ -1,7 +1,7 @@
 """Randomised parity hunt on the GPU box: random FASTQ/FASTA shapes x tables x batch sizes x kernel variants, the CUDA
 path (C ABI) against the CPU oracle, bit for bit.  Test infrastructure (the oracle is the checker).
 
-    python tools/fuzz_gpu.py [--seconds 150] [--seed 1] [--out gpurun_out/fuzz]
+    python tests/fuzz_gpu.py [--seconds 150] [--seed 1] [--out gpurun_out/fuzz]
 
 Every failing case is written to <out>/case_<seed>.bin (+ .json with the parameters) and the run exits 1."""
 from __future__ import annotations

@@ -1,12 +1,12 @@
-"""A fixed slice of the randomised parity hunt (tools/fuzz_gpu.py): random record shapes, line endings, tables, batch
+"""A fixed slice of the randomised parity hunt (tests/fuzz_gpu.py): random record shapes, line endings, tables, batch
 sizes and kernel variants, with and without an injected violation, GPU against oracle.  The open-ended run is
-`python tools/fuzz_gpu.py --seconds N` on the GPU box (723 cases / 2.3 GB without a difference when it was last run)."""
+`python tests/fuzz_gpu.py --seconds N` on the GPU box (723 cases / 2.3 GB without a difference when it was last run)."""
 import os
 import sys
 
 import pytest
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 

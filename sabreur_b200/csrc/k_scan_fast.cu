@@ -62,7 +62,7 @@ constexpr int CNT_BITS = FAST_UNITS == 2 ? 16 : 10;   // per-unit newline counts
 constexpr uint32_t CNT_MASK = (1u << CNT_BITS) - 1u;
 constexpr int FASTA_CHUNKS = (WL_CAP + 31) / 32;
 constexpr uint32_t FASTA_START = 1u << 30;  // list entry flag: a FASTA record starts behind this newline
-constexpr uint32_t POS_MASK = FASTA_START - 1u;  // newline positions per warp slice held in shared memory (>= 16.4-byte lines on average)
+constexpr uint32_t POS_MASK = FASTA_START - 1u;  // the position part of a list entry (batches are at most 1 GiB)
 
 template <int FMT>
 struct FastSmem {
@@ -271,7 +271,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_scan_fast(FastArgs A) {
         for (int s = 0; s < FAST_STAGES; ++s)
             if (t_lo + s < t_hi) issue(s, t_lo + s);
 
-    // Tile loop, ONE block barrier per tile while it is scanned (a second one at its end when single-buffered).  Before it every warp has compacted the newlines of its own
+    // Tile loop, ONE block barrier per tile while it is scanned (a second one at its end when single-buffered).
+    // Before it every warp has compacted the newlines of its own
     // slice and published their number and its last four positions; after it every warp knows its place in the
     // line cycle, fetches the four newlines before its slice and evaluates the records ending in the slice.
     // The barrier of tile t+1 doubles as "everybody is done with tile t", after which thread 0 refills tile
@@ -482,8 +483,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_scan_fast(FastArgs A) {
             if (S.synced && fits && !S.fail) {  // (S.fail: some slice of the CTA may have published nothing usable)
                 const uint32_t h = S.h, fo = S.first_owned;
                 const uint32_t L0 = base + pre_n;  // region-local index of the slice's first newline
-                // entries i of this slice that end a record: (h + L0 + i) % 4 == 3.  TWO lanes per record (a 3 KB
-                // slice ends about ten 150-bp records: one lane each would leave the warp two thirds idle): the even
+                // entries i of this slice that end a record: (h + L0 + i) % 4 == 3.  TWO lanes per record (a 4.5 KB
+                // slice ends about fourteen 150-bp records: one lane each would leave the warp half idle): the even
                 // lane probes around the header's and the record's final newline and packs the first half of the
                 // match window, the odd lane probes around the sequence's newline and packs the second half; one
                 // shuffle pair merges them and the even lane commits.  The loop bounds are warp-uniform so that the

@@ -634,6 +634,12 @@ std::vector<std::string> barcode_list(const Barcode& bd) {
 
 }  // namespace
 
+namespace detail {
+uint64_t host_guess_cut(const uint8_t* p, uint64_t n, uint32_t fmt, uint64_t window) { return guess_cut(p, n, fmt, window); }
+uint64_t host_count_newlines(const uint8_t* p, uint64_t n) { return count_newlines(p, n); }
+void host_canonical_record(const uint8_t* rec, size_t n, uint32_t fmt, std::vector<uint8_t>& out) { canonical_record(rec, n, fmt, out); }
+}  // namespace detail
+
 std::pair<Counts&, bool> se_demux(const std::string& file, Format format, int level, Barcode& bd, uint8_t mismatch,
                                   Counts& nb_records, const HostOptions& opt, RunStats* stats) {
     const Format original = which_format(file);

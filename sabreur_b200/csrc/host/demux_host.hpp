@@ -67,4 +67,13 @@ std::pair<Counts&, std::string> pe_demux(const std::string& forward, const std::
 // src/utils.rs:103-112
 std::vector<std::vector<std::string>> split_by_tab(const std::string& content);
 
+// pure pieces of the host pipeline, exposed for the CPU self-test (host_selftest.cpp, tests/test_host_cpu.py)
+namespace detail {
+// offset where the last (possibly incomplete) record of [p, p + n) is guessed to start, looking back `window` bytes
+uint64_t host_guess_cut(const uint8_t* p, uint64_t n, uint32_t fmt, uint64_t window);
+uint64_t host_count_newlines(const uint8_t* p, uint64_t n);
+// needletail's canonical bytes of one record (src/utils.rs:142-154), appended to `out`
+void host_canonical_record(const uint8_t* rec, size_t n, uint32_t fmt, std::vector<uint8_t>& out);
+}  // namespace detail
+
 }  // namespace sabreur

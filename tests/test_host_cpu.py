@@ -121,3 +121,72 @@ def test_cli_barcode_file_errors(tmp_path):
     two.write_text("ACGT\tbc1_R1.fq\n")
     r = _run([str(two), _fx("test.fq"), _fx("test.fq"), "-o", "o3"], tmp_path)  # paired-end needs three columns
     assert r.returncode == 101
+
+
+# ---- pure pieces of the host pipeline (host_selftest): newline budget, guessed cuts, canonical re-serialisation --------
+HOSTTEST = os.path.join(BIN, "host_selftest")
+
+
+def _host(args, data: bytes) -> bytes:
+    return subprocess.run([HOSTTEST] + [str(a) for a in args], input=data, capture_output=True, check=True).stdout
+
+
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 63, 64, 65, 4096, 64 * 255, 64 * 255 + 1, 64 * 256 + 17, 1_000_003])
+def test_host_newline_count(n):
+    import random
+    rng = random.Random(n)
+    data = bytes(rng.choice(b"\nACGT\n@+I\r") for _ in range(min(n, 70000)))
+    data = (data * (n // max(1, len(data)) + 1))[:n]
+    assert int(_host(["count"], data)) == data.count(b"\n")
+    assert int(_host(["count"], b"\n" * n)) == n  # every byte counter saturating at once
+
+
+def test_host_guessed_cut_is_a_record_start():
+    """the guess may be wrong by design (the GPU verifies it), but on well-formed input -- '@' and '+' opening quality
+    lines included -- it must land on a record start inside the window, and never past the data"""
+    import random
+    rng = random.Random(3)
+    for fastq in (True, False):
+        out, starts = bytearray(), []
+        for i in range(400):
+            L = rng.randint(5, 120)
+            s = bytes(rng.choices(b"ACGT", k=L))
+            starts.append(len(out))
+            if fastq:
+                q = bytearray(rng.choices(range(33, 74), k=L))
+                q[0] = rng.choice(b"@+I")
+                out += b"@r%d\n" % i + s + b"\n+\n" + bytes(q) + b"\n"
+            else:
+                out += b">r%d\n" % i + s[: L // 2] + b"\n" + s[L // 2:] + b"\n"
+        text = bytes(out)
+        for end in [len(text)] + [rng.randrange(2000, len(text)) for _ in range(60)]:
+            cut = int(_host(["cut", 2 if fastq else 1, 1500], text[:end]))
+            assert cut <= end
+            if cut < end:
+                assert cut in starts and cut >= end - 1500, (fastq, end, cut)
+    assert int(_host(["cut", 2, 100], b"ACGT" * 100)) == 400  # no line start in sight: everything stays in the batch
+
+
+def test_host_canonical_record_equals_the_oracle_serialiser():
+    """CRLF line ends, '+id' separator lines, multi-line FASTA, a missing final newline: the host's re-serialisation of a
+    flagged record == the oracle's restatement of needletail's write_fastq / write_fasta (src/utils.rs:142-154)"""
+    import random
+    from oracle import oracle as orc
+    rng = random.Random(11)
+    for fastq in (True, False):
+        for _case in range(60):
+            nl = rng.choice((b"\n", b"\r\n"))
+            L = rng.randint(4, 90)
+            s = bytes(rng.choices(b"ACGTN", k=L))
+            hdr = b"r%d some description" % _case
+            if fastq:
+                plus = rng.choice((b"+", b"+" + hdr))
+                rec = b"@" + hdr + nl + s + nl + plus + nl + bytes(rng.choices(range(33, 74), k=L)) + nl
+            else:
+                w = rng.choice((L, 7, 60, 3))
+                rec = b">" + hdr + nl + b"".join(s[j:j + w] + nl for j in range(0, L, w))
+            if rng.random() < 0.3:
+                rec = rec[:-len(nl)]  # the last record of a stream without a final newline
+            recs, fmt, _ = orc.parse(rec, final=True)
+            assert len(recs) == 1
+            assert _host(["canon", fmt], rec) == orc.serialize(rec, recs[0], fmt), rec

@@ -3,9 +3,14 @@
 #include <dlfcn.h>
 #include <zlib.h>
 
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <stdexcept>
+#include <thread>
 
 namespace sabreur {
 
@@ -125,8 +130,177 @@ const Libs& libs(Format need) {
 
 }  // namespace
 
+// ---- BGZF (blocked gzip, what bgzip / htslib write): every member is a block of <= 64 KiB whose header carries its
+// own compressed size ('BC' extra subfield), so the blocks of a group can be found without inflating and inflated in
+// parallel.  An ordinary gzip stream is sequential by construction and keeps the one-thread path below.
+namespace {
+
+struct BgzfBlock {
+    size_t coff, clen;   // raw deflate data inside the group's compressed buffer
+    size_t ooff;         // where its bytes go in the group's output
+    uint32_t isize, crc;
+};
+
+// 0 = not a BGZF block header; else the total size of the block.  h holds the first 18 bytes of the member when the
+// 'BC' subfield comes first (as every writer emits it); other layouts are scanned from `extra`.
+size_t bgzf_block_size(const uint8_t* h, size_t have, size_t* header_len) {
+    if (have < 18 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return 0;
+    const size_t xlen = h[10] | ((size_t)h[11] << 8);
+    if (have < 12 + xlen) return 0;
+    for (size_t q = 12; q + 4 <= 12 + xlen;) {
+        const size_t slen = h[q + 2] | ((size_t)h[q + 3] << 8);
+        if (h[q] == 'B' && h[q + 1] == 'C' && slen == 2 && q + 6 <= 12 + xlen) {
+            if (h[3] & ~4) return 0;  // a name / comment / header CRC would sit between the extra field and the data
+            *header_len = 12 + xlen;
+            return (size_t)(h[q + 4] | ((size_t)h[q + 5] << 8)) + 1;
+        }
+        q += 4 + slen;
+    }
+    return 0;
+}
+
+class BgzfPool {
+public:
+    explicit BgzfPool(int n) {
+        for (int i = 0; i < n; ++i) th_.emplace_back([this] { work(); });
+    }
+    ~BgzfPool() {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            quit_ = true;
+        }
+        go_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    // inflates blocks[0..n) of `comp` into `out`; throws on corrupt data
+    void run(const uint8_t* comp, uint8_t* out, const BgzfBlock* blocks, size_t n) {
+        std::unique_lock<std::mutex> l(m_);
+        comp_ = comp; out_ = out; blocks_ = blocks; n_ = n;
+        next_.store(0);
+        pending_ = (int)th_.size();
+        bad_ = false;
+        ++gen_;
+        go_.notify_all();
+        done_.wait(l, [this] { return pending_ == 0; });
+        if (bad_) throw std::runtime_error("corrupt gzip stream");
+    }
+
+private:
+    void work() {
+        z_stream z;
+        std::memset(&z, 0, sizeof z);
+        const bool ok = inflateInit2(&z, -15) == Z_OK;  // raw deflate: the block header and trailer are checked here
+        uint64_t seen = 0;
+        while (true) {
+            {
+                std::unique_lock<std::mutex> l(m_);
+                go_.wait(l, [&] { return quit_ || gen_ != seen; });
+                if (quit_) break;
+                seen = gen_;
+            }
+            bool bad = !ok;
+            for (size_t i; !bad && (i = next_.fetch_add(1)) < n_;) {
+                const BgzfBlock& b = blocks_[i];
+                inflateReset(&z);
+                z.next_in = const_cast<Bytef*>(comp_ + b.coff); z.avail_in = (uInt)b.clen;
+                uint8_t spare;  // an empty block (the EOF marker) still needs somewhere to "write"
+                z.next_out = b.isize ? out_ + b.ooff : &spare; z.avail_out = b.isize ? b.isize : 1;
+                const int rc = inflate(&z, Z_FINISH);
+                if (rc != Z_STREAM_END || z.total_out != b.isize || z.avail_in != 0) bad = true;
+                else if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), out_ + b.ooff, b.isize) != b.crc) bad = true;
+            }
+            std::lock_guard<std::mutex> l(m_);
+            if (bad) bad_ = true;
+            if (--pending_ == 0) done_.notify_one();
+        }
+        if (ok) inflateEnd(&z);
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable go_, done_;
+    uint64_t gen_ = 0;
+    int pending_ = 0;
+    bool quit_ = false, bad_ = false;
+    std::atomic<size_t> next_{0};
+    const uint8_t* comp_ = nullptr;
+    uint8_t* out_ = nullptr;
+    const BgzfBlock* blocks_ = nullptr;
+    size_t n_ = 0;
+};
+
+int inflate_threads() {
+    if (const char* e = getenv("SABREUR_INFLATE_THREADS")) return std::max(1, atoi(e));
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(8u, hw ? hw : 1u));
+}
+
+}  // namespace
+
 // ---- Reader ------------------------------------------------------------------------------------------------
 struct Reader::Impl {
+    // BGZF mode: groups of blocks are read, inflated by the pool and served from `group_out`
+    std::unique_ptr<BgzfPool> pool;
+    bool bgzf = false;
+    std::vector<uint8_t> group_comp, group_out;
+    std::vector<BgzfBlock> group_blocks;
+    size_t group_pos = 0, group_len = 0;
+
+    // reads the next group of blocks; false = no further BGZF block (end of file, or an ordinary gzip member follows:
+    // the file position then sits at that member's first byte)
+    bool next_group() {
+        constexpr size_t MAX_BLOCKS = 256;
+        group_blocks.clear();
+        group_comp.clear();
+        size_t out = 0;
+        while (group_blocks.size() < MAX_BLOCKS) {
+            uint8_t h[18];
+            const long at = ftell(f);
+            const size_t got = fread(h, 1, sizeof h, f);
+            if (got == 0) break;  // end of file
+            size_t hlen = 0, total = 0;
+            std::vector<uint8_t> ext;
+            if (got == sizeof h) {
+                total = bgzf_block_size(h, got, &hlen);
+                if (!total && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4)) {  // 'BC' is not the first subfield
+                    const size_t xlen = h[10] | ((size_t)h[11] << 8);
+                    ext.assign(h, h + sizeof h);
+                    ext.resize(12 + xlen < sizeof h ? sizeof h : 12 + xlen);
+                    if (ext.size() > sizeof h && fread(ext.data() + sizeof h, 1, ext.size() - sizeof h, f) != ext.size() - sizeof h)
+                        throw std::runtime_error("truncated compressed stream");
+                    total = bgzf_block_size(ext.data(), ext.size(), &hlen);
+                }
+            }
+            if (!total || total < hlen + 8) {  // not a BGZF block: hand the rest of the file to the sequential decoder
+                fseek(f, at, SEEK_SET);
+                if (group_blocks.empty()) return false;
+                break;
+            }
+            const size_t have = ext.empty() ? sizeof h : ext.size();
+            const size_t base = group_comp.size();
+            group_comp.resize(base + total);
+            std::memcpy(group_comp.data() + base, ext.empty() ? h : ext.data(), std::min(have, total));
+            if (total > have && fread(group_comp.data() + base + have, 1, total - have, f) != total - have)
+                throw std::runtime_error("truncated compressed stream");
+            if (total < have) fseek(f, at + (long)total, SEEK_SET);
+            const uint8_t* t = group_comp.data() + base + total - 8;
+            BgzfBlock b;
+            b.coff = base + hlen;
+            b.clen = total - hlen - 8;
+            b.crc = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+            b.isize = t[4] | (t[5] << 8) | (t[6] << 16) | ((uint32_t)t[7] << 24);
+            if (b.isize > (1u << 16)) throw std::runtime_error("corrupt gzip stream");  // BGZF blocks hold <= 64 KiB
+            b.ooff = out;
+            out += b.isize;
+            group_blocks.push_back(b);
+        }
+        if (group_blocks.empty()) return false;
+        group_out.resize(out);
+        pool->run(group_comp.data(), group_out.data(), group_blocks.data(), group_blocks.size());
+        group_pos = 0;
+        group_len = out;
+        return true;
+    }
+
     FILE* f = nullptr;
     std::vector<uint8_t> in;
     size_t in_pos = 0, in_len = 0;
@@ -151,6 +325,16 @@ Reader::Reader(const std::string& path) : p_(new Impl), fmt_(which_format(path))
     p_->f = fopen(path.c_str(), "rb");
     if (!p_->f) throw std::runtime_error("cannot open '" + path + "'");
     p_->in.resize(1 << 20);
+    if (fmt_ == Format::Gzip) {
+        uint8_t h[18];
+        size_t hlen = 0;
+        const size_t got = fread(h, 1, sizeof h, p_->f);
+        fseek(p_->f, 0, SEEK_SET);
+        if (bgzf_block_size(h, got, &hlen) && inflate_threads() > 1) {
+            p_->bgzf = true;
+            p_->pool.reset(new BgzfPool(inflate_threads()));
+        }
+    }
     if (fmt_ == Format::Zstd) {
         p_->zd = libs(fmt_).ZSTD_createDStream();
         if (!p_->zd) throw std::runtime_error("ZSTD_createDStream failed");
@@ -177,6 +361,16 @@ size_t Reader::read(uint8_t* dst, size_t n) {
     if (n == 0) return 0;
     if (fmt_ == Format::No) return fread(dst, 1, n, I.f);
     size_t got = 0;
+    while (I.bgzf && got < n) {
+        if (I.group_pos == I.group_len && !I.next_group()) {
+            I.bgzf = false;  // end of file, or ordinary gzip members from here on (the loop below takes them)
+            break;
+        }
+        const size_t take = std::min(n - got, I.group_len - I.group_pos);
+        std::memcpy(dst + got, I.group_out.data() + I.group_pos, take);
+        I.group_pos += take;
+        got += take;
+    }
     while (got < n) {
         if (!I.refill()) {
             if (fmt_ == Format::Lzma && I.xz_open) {  // flush the concatenated-stream decoder

@@ -190,3 +190,70 @@ def test_host_canonical_record_equals_the_oracle_serialiser():
             recs, fmt, _ = orc.parse(rec, final=True)
             assert len(recs) == 1
             assert _host(["canon", fmt], rec) == orc.serialize(rec, recs[0], fmt), rec
+
+
+# ---- BGZF (bgzip) input: blocks are inflated in parallel, the result must equal the sequential decoders' ---------------
+def _bgzf(data: bytes, block: int = 65280, level: int = 6, eof: bool = True, extra_first: bytes = b"") -> bytes:
+    """what bgzip writes: gzip members of <= 64 KiB with a 'BC' extra subfield holding the member's size - 1"""
+    import struct
+    import zlib
+    out = bytearray()
+    chunks = [data[i:i + block] for i in range(0, len(data), block)] + ([b""] if eof else [])
+    for c in chunks:
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        raw = co.compress(c) + co.flush()
+        xlen = len(extra_first) + 6
+        bsize = 12 + xlen + len(raw) + 8 - 1
+        out += b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff" + struct.pack("<H", xlen) + extra_first
+        out += b"BC\x02\x00" + struct.pack("<H", bsize) + raw + struct.pack("<II", zlib.crc32(c), len(c))
+    return bytes(out)
+
+
+def _cat(path, chunk=None, threads=None, ok=True):
+    env = dict(os.environ)
+    if threads is not None:
+        env["SABREUR_INFLATE_THREADS"] = str(threads)
+    r = subprocess.run([SELFTEST, "cat", str(path)] + ([str(chunk)] if chunk else []), capture_output=True, env=env)
+    assert (r.returncode == 0) == ok, r.stderr
+    return r.stdout
+
+
+@pytest.mark.parametrize("size", [0, 1, 65279, 65280, 65281, 1_000_000, 40_000_000])
+def test_bgzf_input_decodes_in_parallel(tmp_path, size):
+    import random
+    rng = random.Random(size)
+    line = bytes(rng.choices(b"ACGT", k=150))
+    data = (b"@r\n" + line + b"\n+\n" + bytes(rng.choices(range(33, 74), k=150)) + b"\n") * (size // 306 + 1)
+    data = data[:size]
+    p = tmp_path / "in.fq.gz"
+    p.write_bytes(_bgzf(data))
+    assert gzip.decompress(p.read_bytes()) == data  # the writer above is a valid gzip file
+    for threads, chunk in ((None, None), (4, 1000), (1, None)):  # 1 thread = the sequential decoder on the same file
+        assert _cat(p, chunk, threads) == data
+
+
+def test_bgzf_variants_and_mixed_files(tmp_path):
+    data = b"".join(b">s%d\nACGTACGTAC\n" % i for i in range(30000))
+    p = tmp_path / "x.gz"
+    # the 'BC' subfield behind another one; no EOF marker; an ordinary gzip member appended; BGZF after an ordinary member
+    p.write_bytes(_bgzf(data, extra_first=b"XY\x03\x00abc"))
+    assert _cat(p) == data
+    p.write_bytes(_bgzf(data, eof=False))
+    assert _cat(p) == data
+    p.write_bytes(_bgzf(data, block=10000) + gzip.compress(b"tail1\n") + _bgzf(b"tail2\n"))
+    assert _cat(p) == data + b"tail1\ntail2\n"
+    p.write_bytes(gzip.compress(b"head\n") + _bgzf(data))
+    assert _cat(p) == b"head\n" + data
+
+
+def test_bgzf_corruption_is_an_error(tmp_path):
+    data = b"".join(b">s%d\nACGTACGTAC\n" % i for i in range(30000))
+    good = _bgzf(data)
+    p = tmp_path / "bad.gz"
+    p.write_bytes(good[: len(good) // 2])                       # cut inside a block
+    assert b"truncated" in subprocess.run([SELFTEST, "cat", str(p)], capture_output=True).stderr
+    bad = bytearray(good)
+    bad[len(good) // 3] ^= 0x55                                 # a flipped byte inside some block's deflate data
+    p.write_bytes(bytes(bad))
+    r = subprocess.run([SELFTEST, "cat", str(p)], capture_output=True)
+    assert r.returncode != 0 and b"corrupt" in r.stderr

@@ -20,11 +20,24 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def bgzf_blocks(data: bytes, eof: bool = False) -> bytes:
+    """gzip members of <= 64 KiB carrying their own size in a 'BC' extra subfield (the BGZF layout of bgzip / htslib)"""
+    import struct
+    import zlib
+    out = bytearray()
+    for c in [data[i:i + 65280] for i in range(0, len(data), 65280)] + ([b""] if eof else []):
+        co = zlib.compressobj(1, zlib.DEFLATED, -15)
+        raw = co.compress(c) + co.flush()
+        out += b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", 18 + len(raw) + 8 - 1)
+        out += raw + struct.pack("<II", zlib.crc32(c), len(c))
+    return bytes(out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--reads", type=int, default=4_000_000)
-    ap.add_argument("--in-format", default="gz", choices=["gz", "plain"])
+    ap.add_argument("--in-format", default="gz", choices=["gz", "bgzf", "plain"])  # bgzf: blocked gzip as bgzip writes it
     ap.add_argument("--out-format", default="none", choices=["none", "gz", "zst", "bz2", "xz"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--batch-mb", type=int, default=256)
@@ -35,11 +48,14 @@ def main():
     with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
         paths = []
         for mate in ((0, 1) if w.paired else (0,)):
-            p = os.path.join(d, f"in_R{mate + 1}." + ("fa" if w.fmt == 1 else "fq") + (".gz" if a.in_format == "gz" else ""))
+            p = os.path.join(d, f"in_R{mate + 1}." + ("fa" if w.fmt == 1 else "fq") + ("" if a.in_format == "plain" else ".gz"))
             opener = (lambda q: gzip.open(q, "wb", compresslevel=1)) if a.in_format == "gz" else (lambda q: open(q, "wb"))
             with opener(p) as fh:
                 for lo in range(0, a.reads, 500_000):
-                    fh.write(synth.reads_host(w, tab, lo, min(500_000, a.reads - lo), mate).tobytes())
+                    text = synth.reads_host(w, tab, lo, min(500_000, a.reads - lo), mate).tobytes()
+                    fh.write(bgzf_blocks(text) if a.in_format == "bgzf" else text)
+                if a.in_format == "bgzf":
+                    fh.write(bgzf_blocks(b"", eof=True))
             paths.append(p)
         tsv = os.path.join(d, "bc.tsv")
         with open(tsv, "w") as fh:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SBR_ABI_VERSION 1
+#define SBR_ABI_VERSION 2
 
 typedef enum {
     SBR_OK = 0,
@@ -63,6 +63,9 @@ typedef enum {
 #define SBR_CFG_TIMING   0x4u  /* record CUDA events around every kernel: see sbr_timing_collect() */
 #define SBR_CFG_EXACT_SCAN 0x8u /* skip the region-parallel scan: always run the look-back scan */
 #define SBR_CFG_NO_FUSE 0x10u   /* run match and partition as separate launches (default: one cooperative launch) */
+#define SBR_CFG_OVERLAP 0x20u   /* device-resident batches (sbr_demux_device): match + partition of a batch run on a
+                                   stream of the slot's own, beside the NEXT batch's record scan on the caller's stream;
+                                   see sbr_device_join() */
 
 typedef struct sbr_ctx sbr_ctx;
 
@@ -108,8 +111,9 @@ void sbr_destroy(sbr_ctx* ctx);
 const char* sbr_last_error(const sbr_ctx* ctx); /* ctx may be NULL: last create() failure */
 
 /* ---- streaming path: pinned host slots -> GPU -> pinned results --------------------------------
- * sbr_slot_buffer: the pinned host buffer of a slot (capacity = batch_bytes + 64).  The host
- * decompressor writes text straight into it.
+ * sbr_slot_buffer: the pinned host buffer of a slot.  *capacity = batch_bytes is what the caller may fill; the
+ * allocation is 64 bytes larger, and that padding belongs to the library (final-newline patch, 16-byte
+ * zero fill).  The host decompressor writes text straight into the buffer.
  * sbr_submit: asynchronous H2D copy -> record scan -> match -> partition -> D2H of the results.
  * The batch is host_ptr[offset .. offset+nbytes) (offset + nbytes <= capacity): a host that reserves
  * room at the front of a slot can prepend the unconsumed tail of the previous batch without moving
@@ -134,6 +138,14 @@ int sbr_wait(sbr_ctx* ctx, uint32_t slot, sbr_result* res);
 int sbr_demux_device(sbr_ctx* ctx, uint32_t slot, const uint8_t* d_text, uint64_t nbytes,
                      int final_batch, void* stream);
 int sbr_slot_device_result(sbr_ctx* ctx, uint32_t slot, sbr_result* res_device_ptrs);
+/* SBR_CFG_OVERLAP: makes `stream` wait for the match + partition work still outstanding on the slots' own
+ * streams (one cudaStreamWaitEvent per slot; nothing blocks on the host).  Call it before recording the event
+ * that ends a timed region, or before work on `stream` that reads the device results.  A no-op otherwise. */
+int sbr_device_join(sbr_ctx* ctx, void* stream);
+/* Device-side counters of the region-parallel scan since the context was created (or last reset):
+ * out[0] = batches it finished, out[1] = batches it handed over to the exact look-back scan (these read
+ * "no records" on the device until sbr_wait() has re-run them).  Synchronises the device. */
+int sbr_scan_stats(sbr_ctx* ctx, uint64_t out[2], int reset);
 
 /* The first-match lookup table built from the barcode table (debug / test access).
  * Returns the number of entries (4^bc_len) or 0 when the context does not use a LUT. */

@@ -38,10 +38,10 @@ REC_DTYPE = np.dtype([(n, "<u8") for n in
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "sabreur_oracle.c")
+    srcs = [os.path.join(_HERE, f) for f in ("sabreur_oracle.c", "synth_ref.c")]
     hdr = os.path.join(_HERE, "sabreur_oracle.h")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        subprocess.check_call(["gcc", "-O2", "-fPIC", "-std=c11", "-shared", "-o", so, src])
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs + [hdr]):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-std=c11", "-shared", "-o", so] + srcs)
     return so
 
 
@@ -69,8 +69,49 @@ def lib():
         L.orc_demux_stream.restype = C.c_long
         L.orc_fnv1a.argtypes = [u8p, C.c_size_t, C.c_uint64]
         L.orc_fnv1a.restype = C.c_uint64
+        L.orc_synth_table.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u8p]
+        L.orc_synth_table.restype = C.c_int
+        L.orc_synth_record_bytes.argtypes = [C.c_int, C.c_uint32]
+        L.orc_synth_record_bytes.restype = C.c_uint32
+        L.orc_synth_reads.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, u8p, C.c_uint32, C.c_uint32,
+                                      C.c_uint64, C.c_uint64, u8p]
+        L.orc_synth_reads.restype = C.c_int
         _LIB = L
     return _LIB
+
+
+def synth_table(seed: int, n_barcodes: int, bc_len: int, min_dist: int) -> np.ndarray:
+    """greedy min-distance barcode table (oracle/synth_ref.c)"""
+    out = np.zeros((n_barcodes, bc_len), dtype=np.uint8)
+    if lib().orc_synth_table(seed, n_barcodes, bc_len, min_dist, out.ctypes.data) != 0:
+        raise RuntimeError("orc_synth_table failed")
+    return out
+
+
+def synth_reads(fmt: int, read_len: int, mate: int, seed: int, table: np.ndarray, first: int, n: int,
+                threads: int = 1) -> np.ndarray:
+    """records [first, first + n) of the synthetic stream (oracle/synth_ref.c); `threads` > 1 fills
+    disjoint ranges in parallel (ctypes releases the GIL)"""
+    L = lib()
+    rec = L.orc_synth_record_bytes(int(fmt == FMT_FASTQ), read_len)
+    out = np.empty(n * rec, dtype=np.uint8)
+    tab = np.ascontiguousarray(table, dtype=np.uint8)
+
+    def fill(lo, hi):
+        rc = L.orc_synth_reads(int(fmt == FMT_FASTQ), read_len, mate, seed, tab.ctypes.data, tab.shape[0], tab.shape[1],
+                               first + lo, hi - lo, out.ctypes.data + lo * rec)
+        if rc != 0:
+            raise RuntimeError("orc_synth_reads failed")
+
+    if threads <= 1 or n < 4 * threads:
+        fill(0, n)
+    else:
+        import threading
+        per = (n + threads - 1) // threads
+        ths = [threading.Thread(target=fill, args=(i * per, min(n, (i + 1) * per))) for i in range(threads) if i * per < n]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+    return out
 
 
 class OracleError(Exception):

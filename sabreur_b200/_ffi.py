@@ -12,13 +12,13 @@ SBR_OK = 0
 ST_INVALID_START, ST_INVALID_SEP, ST_UNEQUAL_LEN, ST_SHORT_READ = 0x01, 0x02, 0x04, 0x08
 ST_TRUNCATED, ST_REC_OVERFLOW, ST_NONCANONICAL, ST_ERROR_MASK = 0x10, 0x20, 0x40, 0x1F
 FMT_AUTO, FMT_FASTA, FMT_FASTQ = 0, 1, 2
-CFG_NO_LUT, CFG_GENERIC, CFG_TIMING, CFG_EXACT_SCAN, CFG_NO_FUSE = 0x1, 0x2, 0x4, 0x8, 0x10
+CFG_NO_LUT, CFG_GENERIC, CFG_TIMING, CFG_EXACT_SCAN, CFG_NO_FUSE, CFG_OVERLAP = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 KEY_SHORT, KEY_NONCANON = 1 << 48, 1 << 49
 
 # every symbol include/sabreur_gpu.h declares
 EXPORTS = [
     "sbr_abi_version", "sbr_device_count", "sbr_create", "sbr_destroy", "sbr_last_error", "sbr_slot_buffer",
-    "sbr_submit", "sbr_wait", "sbr_demux_device", "sbr_slot_device_result", "sbr_lut_entries", "sbr_lut_copy",
+    "sbr_submit", "sbr_wait", "sbr_demux_device", "sbr_slot_device_result", "sbr_device_join", "sbr_scan_stats", "sbr_lut_entries", "sbr_lut_copy",
     "sbr_debug_regions", "sbr_timing_collect", "sbr_synth_table", "sbr_synth_record_bytes", "sbr_synth_host", "sbr_synth_device",
     "sbr_dev_alloc", "sbr_dev_free", "sbr_dev_upload", "sbr_dev_download", "sbr_host_alloc_pinned",
     "sbr_host_free_pinned",
@@ -69,6 +69,8 @@ def load():
         "sbr_wait": (i32, [vp, u32, C.POINTER(SbrResult)]),
         "sbr_demux_device": (i32, [vp, u32, vp, u64, i32, vp]),
         "sbr_slot_device_result": (i32, [vp, u32, C.POINTER(SbrResult)]),
+        "sbr_device_join": (i32, [vp, vp]),
+        "sbr_scan_stats": (i32, [vp, C.POINTER(u64 * 2), i32]),
         "sbr_lut_entries": (u64, [vp]),
         "sbr_lut_copy": (i32, [vp, vp, u64]),
         "sbr_debug_regions": (i32, [vp, u32, vp, u32]),

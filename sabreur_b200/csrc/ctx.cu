@@ -1,5 +1,6 @@
 // ctx.cu -- host side of the C ABI (include/sabreur_gpu.h): contexts, slots, streams, copies.
 // No CPU compute path lives here: if CUDA is unavailable every entry point fails loudly.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -20,12 +21,13 @@ cudaError_t scan_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbytes, ui
 uint32_t scan_tiles(uint32_t nbytes);
 // k_scan_fast.cu (region-parallel scan)
 cudaError_t scan_fast_prepare(int device, int* grid_fastq, int* grid_fasta);
+size_t scan_fast_smem_bytes(uint32_t fmt);
 uint32_t scan_fast_regions(uint32_t nbytes, int max_regions, uint32_t* tiles_per_region, uint32_t* extra_regions);
 cudaError_t scan_fast_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbytes, uint32_t max_records, uint32_t cap_r,
                              uint32_t n_regions, uint32_t tiles_per_region, uint32_t extra_regions, uint32_t bc_len,
                              uint32_t packed, uint32_t final_batch, BatchHeader* hdr, RegionInfo* info, uint32_t* region_base,
                              uint32_t* seg_rec_off, uint64_t* seg_key, uint32_t* rec_off_dense, uint4* lookback_desc,
-                             uint32_t n_desc, cudaStream_t stream);
+                             uint32_t n_desc, uint32_t* stats, cudaStream_t stream);
 // k_match.cu
 struct MatchLaunch {
     const uint64_t* key_dense; const uint64_t* seg_key; const uint32_t* seg_rec_off; const uint32_t* region_base;
@@ -37,6 +39,7 @@ struct MatchLaunch {
     uint16_t* assign; uint32_t* rec_off; uint64_t* key_out; uint32_t* cta_cnt; uint32_t nbins;
     int grid;
     int fused; uint32_t nbits; uint32_t* bin_count; uint32_t* bin_start; uint32_t* order; BatchHeader* zero_next;
+    uint32_t force_keys;
 };
 size_t match_smem(uint32_t n, uint32_t stride, uint32_t nbins, bool generic);
 cudaError_t match_prepare();
@@ -64,10 +67,16 @@ static thread_local std::string g_create_error;
 namespace {
 
 constexpr int TIMING_RING = 2048;
+constexpr int EV_PER = 5;
 
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t hdr_ready = nullptr;
+    // overlapped mode (SBR_CFG_OVERLAP, device-resident batches): match + partition run on `aux` beside the NEXT batch's scan
+    cudaStream_t aux = nullptr;
+    cudaEvent_t scan_done = nullptr;  // recorded behind the scan on the caller's stream; `aux` waits for it
+    cudaEvent_t mp_done = nullptr;    // recorded behind match + partition on `aux`; the slot's next scan waits for it
+    bool mp_pending = false;
     // device
     uint8_t* d_text = nullptr;
     BatchHeader* d_hdr = nullptr;   // the header of the batch in flight: one of d_hdr2[0..1], alternating
@@ -135,11 +144,13 @@ struct sbr_ctx {
     uint64_t lut_entries = 0;
     PartitionPlan plan{};
     bool fused = false;  // match + partition in one cooperative launch
+    bool overlap = false;  // device-resident batches: match + partition on the slot's aux stream, beside the next scan
+    uint32_t* d_stats = nullptr;  // {batches the region-parallel scan finished, batches it handed to the exact scan, 0, 0}
     std::vector<Slot> slots;
     std::string err;
     // timing ring
     bool timing = false;
-    std::vector<cudaEvent_t> ev;  // 4 per batch
+    std::vector<cudaEvent_t> ev;  // EV_PER per batch: scan start, scan end, match end, partition end, match start (overlapped mode)
     int ev_used = 0;
     uint64_t launches = 0;
 };
@@ -184,7 +195,11 @@ static void free_slot(Slot& s) {
     cudaFree(s.d_assign); cudaFree(s.d_cta_cnt); cudaFree(s.d_bin_count); cudaFree(s.d_bin_start); cudaFree(s.d_order);
     cudaFreeHost(s.h_text); cudaFreeHost(s.h_hdr); cudaFreeHost(s.h_rec_off); cudaFreeHost(s.h_key);
     cudaFreeHost(s.h_assign); cudaFreeHost(s.h_bin_count); cudaFreeHost(s.h_bin_start); cudaFreeHost(s.h_order);
+    if (s.aux) cudaStreamSynchronize(s.aux);
     if (s.hdr_ready) cudaEventDestroy(s.hdr_ready);
+    if (s.scan_done) cudaEventDestroy(s.scan_done);
+    if (s.mp_done) cudaEventDestroy(s.mp_done);
+    if (s.aux) cudaStreamDestroy(s.aux);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
 }
@@ -195,6 +210,7 @@ extern "C" void sbr_destroy(sbr_ctx* c) {
     for (auto& s : c->slots) free_slot(s);
     for (auto e : c->ev) cudaEventDestroy(e);
     cudaFree(c->d_tab); cudaFree(c->d_rows); cudaFree(c->d_lens); cudaFree(c->d_lut); cudaFree(c->d_lut1);
+    cudaFree(c->d_stats);
     delete c;
 }
 
@@ -251,6 +267,28 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
     c->plan = partition_plan(c->nbins, c->max_records, c->sms);
     if (match_smem(n, k, c->nbins, !c->packed) > 200 * 1024) return fail(c, SBR_E_UNSUPPORTED, "barcode table too large");
     const bool will_lut = c->packed && !(cfg->flags & SBR_CFG_NO_LUT) && k <= 12;
+    c->overlap = (cfg->flags & SBR_CFG_OVERLAP) != 0;
+    if (c->overlap) {
+        // does one match CTA fit on an SM beside four CTAs of the scan?  (228 KB of shared memory per SM, 1 KB reserved per
+        // CTA.)  If it does not -- a table of more than ~800 bins -- the kernels would take turns instead of sharing
+        // the SMs, which is slower than running them back to back: fall back to one stream.
+        size_t scan_smem = 0;
+        for (uint32_t f = SBR_FMT_FASTA; f <= SBR_FMT_FASTQ; ++f)
+            if (cfg->fmt == SBR_FMT_AUTO || cfg->fmt == f) scan_smem = std::max(scan_smem, scan_fast_smem_bytes(f));
+        const size_t need = 4 * (scan_smem + 1024) + match_smem(n, k, c->nbins, !c->packed) + 1024;
+        if (need > 228 * 1024 && !getenv("SBR_OVERLAP_FORCE")) c->overlap = false;
+    }
+    if (c->overlap) {
+        // match + partition of batch i run beside the scan of batch i+1: the scan holds 4 CTAs x 256 threads x 48
+        // registers and ~47 KB of shared memory each on every SM, which leaves room for exactly one 256-thread CTA of
+        // the match kernel (<= 64 registers, <= 34 KB).  One CTA per SM is slow when it runs alone, but it only has to
+        // finish within the next scan's time.
+        int per_sm = 1;
+        if (const char* e = getenv("SBR_MP_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : 1;
+        const uint32_t want = (c->max_records + 256u * 4u - 1u) / (256u * 4u);
+        c->plan.grid = (int)std::max(1u, std::min(want, (uint32_t)(c->sms * per_sm)));
+        c->plan.V = (uint32_t)c->plan.grid * 8u;
+    }
     if (!(cfg->flags & SBR_CFG_NO_FUSE)) {
         // kernel 3 rides in the match kernel's launch when the whole grid can be resident at once
         const int cap = match_fused_max_grid(cfg->device, !c->packed ? 2 : (will_lut ? 0 : 1), match_smem(n, k, c->nbins, !c->packed));
@@ -289,11 +327,20 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
         CU(c, cudaMemcpy(c->d_lens, c->lens.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
 
+    CU(c, cudaMalloc(&c->d_stats, 4 * sizeof(uint32_t)));
+    CU(c, cudaMemset(c->d_stats, 0, 4 * sizeof(uint32_t)));
     c->slots.resize(cfg->n_slots);
     const size_t mr = c->max_records;
+    int prio_lo = 0, prio_hi = 0;
+    CU(c, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     for (auto& s : c->slots) {
         CU(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CU(c, cudaEventCreateWithFlags(&s.hdr_ready, cudaEventDisableTiming));
+        if (c->overlap) {  // the small kernels beside the scan go first whenever they are ready
+            CU(c, cudaStreamCreateWithPriority(&s.aux, cudaStreamNonBlocking, prio_hi));
+            CU(c, cudaEventCreateWithFlags(&s.scan_done, cudaEventDisableTiming));
+            CU(c, cudaEventCreateWithFlags(&s.mp_done, cudaEventDisableTiming));
+        }
         CU(c, cudaMalloc(&s.d_hdr2, 2 * sizeof(BatchHeader)));
         CU(c, cudaMemset(s.d_hdr2, 0, 2 * sizeof(BatchHeader)));
         s.d_hdr = s.d_hdr2;
@@ -318,7 +365,7 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
         memset(s.h_hdr, 0, sizeof(BatchHeader));
     }
     if (c->timing) {
-        c->ev.resize((size_t)TIMING_RING * 4);
+        c->ev.resize((size_t)TIMING_RING * EV_PER);
         for (auto& ev : c->ev) CU(c, cudaEventCreate(&ev));
     }
     return SBR_OK;
@@ -382,6 +429,7 @@ static int launch_match_partition(sbr_ctx* c, Slot& s, const uint8_t* d_text, ui
     L.fused = c->fused ? 1 : 0; L.nbits = c->plan.nbits;
     L.bin_count = s.d_bin_count; L.bin_start = s.d_bin_start; L.order = s.d_order;
     L.zero_next = s.d_hdr2 + (s.hdr_idx ^ 1u);
+    L.force_keys = s.supplied_nl ? 1u : 0u;  // sbr_wait flags the patched last record: every scan word must be there
     CU(c, match_launch(L, st));
     if (ev) CU(c, cudaEventRecord(ev[2], st));
     if (!c->fused)
@@ -397,9 +445,14 @@ static int launch_match_partition(sbr_ctx* c, Slot& s, const uint8_t* d_text, ui
 // run over nothing, and sbr_wait() re-runs the batch through the exact look-back scan (rerun_exact below).  A clean
 // batch therefore never pays for a launch of the fallback.
 static int launch_pipeline(sbr_ctx* c, Slot& s, const uint8_t* d_text, uint32_t nbytes, uint32_t fmt, int final_batch,
-                           cudaStream_t st) {
+                           cudaStream_t st, bool overlap) {
     cudaEvent_t* ev = nullptr;
-    if (c->timing && c->ev_used < TIMING_RING) ev = &c->ev[(size_t)c->ev_used++ * 4];
+    if (c->timing && c->ev_used < TIMING_RING) ev = &c->ev[(size_t)c->ev_used++ * EV_PER];
+    // overlapped: the slot's previous match + partition (on its aux stream) still read the arrays this scan rewrites
+    if (s.mp_pending) {
+        if (st != s.aux) CU(c, cudaStreamWaitEvent(st, s.mp_done, 0));
+        s.mp_pending = false;
+    }
     // the header: the slot's two alternate; this batch takes the one the previous batch's last kernel cleared
     s.hdr_idx ^= 1u;
     s.d_hdr = s.d_hdr2 + s.hdr_idx;
@@ -419,11 +472,21 @@ static int launch_pipeline(sbr_ctx* c, Slot& s, const uint8_t* d_text, uint32_t 
         // (k_scan_finish clears the look-back scan's tile descriptors when it hands the batch over)
         CU(c, scan_fast_launch(fmt, d_text, nbytes, c->max_records, s.cur_cap_r, nreg, tpr, extra, c->cfg.bc_len,
                                c->packed ? 1u : 0u, (uint32_t)final_batch, s.d_hdr, s.d_info, s.d_region_base, s.d_seg_rec_off,
-                               s.d_seg_key, s.d_rec_off, s.d_desc, scan_tiles(nbytes), st));
-        c->launches += 2;
+                               s.d_seg_key, s.d_rec_off, s.d_desc, scan_tiles(nbytes), c->d_stats, st));
+        c->launches += 1;
     }
     if (ev) CU(c, cudaEventRecord(ev[1], st));
-    return launch_match_partition(c, s, d_text, nbytes, s.cur_cap_r, st, ev);
+    if (ev && !overlap) CU(c, cudaEventRecord(ev[4], st));
+    if (!overlap) return launch_match_partition(c, s, d_text, nbytes, s.cur_cap_r, st, ev);
+    // match + partition on the slot's aux stream: the caller's stream is free for the next batch's scan at once
+    CU(c, cudaEventRecord(s.scan_done, st));
+    CU(c, cudaStreamWaitEvent(s.aux, s.scan_done, 0));
+    if (ev) CU(c, cudaEventRecord(ev[4], s.aux));  // match + partition are timed on their own stream: ev[4] -> ev[2] -> ev[3]
+    int rc = launch_match_partition(c, s, d_text, nbytes, s.cur_cap_r, s.aux, ev);
+    if (rc) return rc;
+    CU(c, cudaEventRecord(s.mp_done, s.aux));
+    s.mp_pending = true;
+    return SBR_OK;
 }
 
 // the region-parallel scan handed the batch over: exact look-back scan, then match and partition again
@@ -493,7 +556,7 @@ extern "C" int sbr_submit(sbr_ctx* c, uint32_t slot, uint64_t offset, uint64_t n
         memset(h + eff, 0, 16);
         uint64_t copy = (eff + 15) & ~15ull;
         CU(c, cudaMemcpyAsync(s.d_text, h, copy, cudaMemcpyHostToDevice, s.stream));
-        rc = launch_pipeline(c, s, s.d_text, (uint32_t)eff, fmt, final_batch, s.stream);
+        rc = launch_pipeline(c, s, s.d_text, (uint32_t)eff, fmt, final_batch, s.stream, false);
         if (rc) return rc;
         CU(c, cudaMemcpyAsync(s.h_hdr, s.d_hdr, sizeof(BatchHeader), cudaMemcpyDeviceToHost, s.stream));
         CU(c, cudaMemcpyAsync(s.h_bin_count, s.d_bin_count, c->nbins * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
@@ -521,12 +584,32 @@ extern "C" int sbr_demux_device(sbr_ctx* c, uint32_t slot, const uint8_t* d_text
     s.final_batch = final_batch;
     s.fmt = c->cfg.fmt;
     s.host_error = false;
-    s.last_stream = st;
+    s.last_stream = c->overlap ? s.aux : st;
     s.via_submit = false;
     s.supplied_nl = false;
-    int rc = launch_pipeline(c, s, d_text, (uint32_t)nbytes, c->cfg.fmt, final_batch, st);
+    int rc = launch_pipeline(c, s, d_text, (uint32_t)nbytes, c->cfg.fmt, final_batch, st, c->overlap);
     if (rc) return rc;
     s.in_flight = true;
+    return SBR_OK;
+}
+
+extern "C" int sbr_device_join(sbr_ctx* c, void* stream) {
+    if (!c) return fail(c, SBR_E_INVALID_ARG, "bad argument");
+    CU(c, cudaSetDevice(c->device));
+    for (auto& s : c->slots)
+        if (s.mp_pending) CU(c, cudaStreamWaitEvent((cudaStream_t)stream, s.mp_done, 0));
+    return SBR_OK;
+}
+
+extern "C" int sbr_scan_stats(sbr_ctx* c, uint64_t out[2], int reset) {
+    if (!c || !out) return fail(c, SBR_E_INVALID_ARG, "bad argument");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaDeviceSynchronize());
+    uint32_t h[4] = {0, 0, 0, 0};
+    CU(c, cudaMemcpy(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+    out[0] = h[0];
+    out[1] = h[1];
+    if (reset) CU(c, cudaMemset(c->d_stats, 0, sizeof h));
     return SBR_OK;
 }
 
@@ -657,10 +740,11 @@ extern "C" int sbr_timing_collect(sbr_ctx* c, double ms[3], uint64_t* batches, u
     CU(c, cudaDeviceSynchronize());
     ms[0] = ms[1] = ms[2] = 0.0;
     for (int i = 0; i < c->ev_used; ++i) {
-        cudaEvent_t* ev = &c->ev[(size_t)i * 4];
+        cudaEvent_t* ev = &c->ev[(size_t)i * EV_PER];
+        const int from[3] = {0, 4, 2}, to[3] = {1, 2, 3};
         for (int k = 0; k < 3; ++k) {
             float t = 0.f;
-            CU(c, cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
+            CU(c, cudaEventElapsedTime(&t, ev[from[k]], ev[to[k]]));
             ms[k] += t;
         }
     }

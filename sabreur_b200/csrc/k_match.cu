@@ -85,6 +85,7 @@ struct MatchArgs {
     // FUSED only: kernel 3's outputs
     uint32_t nbits; uint32_t* bin_count; uint32_t* bin_start; uint32_t* order;
     BatchHeader* zero_next;  // the slot's other header: cleared here for the next batch (saves a memset per batch)
+    uint32_t force_keys;
 };
 
 // lanes holding the same bin as this lane, from one ballot per bit of the bin index (same as k_partition.cu)
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(const MatchArgs A) {
     const uint32_t nrec = hdr->n_records;
     const bool fasta = hdr->fmt == SBR_FMT_FASTA;
     // the host asks for the per-record scan words only when some record needs re-serialisation
-    const bool want_keys = mode && (hdr->status & SBR_ST_NONCANONICAL);
+    const bool want_keys = mode && ((hdr->status & SBR_ST_NONCANONICAL) || A.force_keys);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t V = gridDim.x * WARPS, v = blockIdx.x * WARPS + warp;
     uint32_t* mine = s_hist + (size_t)warp * nbins;
@@ -400,6 +401,7 @@ struct MatchLaunch {
     int grid;  // = the partition plan's grid: the histogram slices are kernel 3's slices
     // fused with kernel 3 (cooperative launch) when `fused`
     int fused; uint32_t nbits; uint32_t* bin_count; uint32_t* bin_start; uint32_t* order; BatchHeader* zero_next;
+    uint32_t force_keys;  // write key_out whatever the header says (the host patched the stream's last record)
 };
 
 size_t match_smem(uint32_t n, uint32_t stride, uint32_t nbins, bool generic) {
@@ -452,6 +454,7 @@ cudaError_t match_launch(const MatchLaunch& L, cudaStream_t stream) {
     A.assign = L.assign; A.rec_off = L.rec_off; A.key_out = L.key_out; A.cta_cnt = L.cta_cnt; A.nbins = L.nbins;
     A.nbits = L.nbits; A.bin_count = L.bin_count; A.bin_start = L.bin_start; A.order = L.order;
     A.zero_next = L.fused ? L.zero_next : nullptr;
+    A.force_keys = L.force_keys;
     const size_t smem = match_smem(L.n, L.stride, L.nbins, generic);
     if (L.fused) {
         void* args[] = {&A};

@@ -86,6 +86,7 @@ struct FastSmem {
     uint32_t fail;
     uint32_t done;         // FASTQ: the record open at the region's end has been finished
     uint32_t crlf;
+    uint32_t is_last;      // this CTA was the last of the grid to finish its region: it runs the batch's epilogue
     unsigned long long wlast[FAST_WARPS];  // FASTA, per warp: (newlines up to the one before its last record start) << 32 | offset
 };
 
@@ -105,6 +106,13 @@ struct FastArgs {
     RegionInfo* info;
     uint32_t* seg_rec_off;
     uint64_t* seg_key;
+    // the batch's epilogue (run by the last CTA to finish, see scan_finish)
+    uint32_t max_records;
+    uint32_t n_desc;
+    uint32_t* region_base;    // [n_regions + 1]
+    uint32_t* rec_off_dense;
+    uint4* lookback_desc;
+    uint32_t* stats;          // context-wide counters: [0] batches finished here, [1] batches handed to the exact scan
 };
 
 // 0x80 in every byte of w equal to the splatted byte `cx` (cx < 0x80): three instructions
@@ -202,9 +210,117 @@ __device__ __noinline__ uint64_t fastq_slow(const uint8_t* sm, const uint8_t* te
     return key | ((uint64_t)bits << 56);
 }
 
-// KW: 32-bit words of text covering the match window (ceil(bc_len / 4), 1..4) in packed mode; 0 = unpacked keys
+// The batch's epilogue, run by the CTA that finishes its region last (an atomic ticket in the header, so no
+// second launch): verifies every region against exact prefix sums and publishes the batch header.
+//   * FASTQ: a region's detected phase must equal (newlines before the region) mod 4;
+//   * any region that met something the fast path does not handle, or more records than max_records, hands the
+//     whole batch to the exact look-back scan (hdr->spec_fail).
+// Every thread owns RPT consecutive regions; `sc` is scratch shared memory (>= 32 words).
+template <int FMT>
+__device__ __forceinline__ void scan_finish(const FastArgs& A, uint32_t n_regions, uint32_t* sc) {
+    constexpr int RPT = (MAX_REGIONS + FAST_THREADS - 1) / FAST_THREADS;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t nl[RPT], nr[RPT], ph[RPT], fl[RPT];
+    uint32_t snl = 0, srec = 0;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        const uint32_t c = tid * RPT + j;
+        nl[j] = nr[j] = fl[j] = 0u;
+        ph[j] = PHASE_UNKNOWN;
+        if (c < n_regions) {  // written by other CTAs before their ticket: read past L1
+            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(A.info + c));
+            nl[j] = v.x; nr[j] = v.y; ph[j] = v.z; fl[j] = v.w;
+        }
+        snl += nl[j];
+        srec += nr[j];
+    }
+    if (tid == 0) { sc[16] = 0u; sc[17] = 0u; sc[18] = 0u; }  // fail, last region with records, newlines before it
+    const uint32_t inl = warp_incl_scan(snl, lane), irec = warp_incl_scan(srec, lane);
+    if (lane == 31) { sc[warp] = inl; sc[8 + warp] = irec; }
+    __syncthreads();
+    uint32_t nl_before = inl - snl, rec_before = irec - srec, total_nl = 0, total_rec = 0;
+#pragma unroll
+    for (int w = 0; w < FAST_WARPS; ++w) {
+        const uint32_t a = sc[w], b = sc[8 + w];
+        if (w < (int)warp) { nl_before += a; rec_before += b; }
+        total_nl += a;
+        total_rec += b;
+    }
+    bool bad = false;
+    uint32_t my_last = 0, my_last_nlb = 0;
+    bool have = false;
+    {
+        uint32_t nlb = nl_before, rb = rec_before;
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const uint32_t c = tid * RPT + j;
+            if (c < n_regions) {
+                if (fl[j] & 1u) bad = true;
+                if (FMT == SBR_FMT_FASTQ) {
+                    if (ph[j] == PHASE_UNKNOWN) bad |= nl[j] != 0;  // lines it could not place
+                    else bad |= ph[j] != (nlb & 3u);                // detected phase vs the exact one
+                }
+                if (nr[j]) { have = true; my_last = c; my_last_nlb = nlb; }
+                A.region_base[c] = rb;
+            }
+            nlb += nl[j];
+            rb += nr[j];
+        }
+    }
+    if (bad) sc[16] = 1u;
+    if (have) atomicMax(&sc[17], my_last);
+    __syncthreads();
+    if (have && my_last == sc[17]) sc[18] = my_last_nlb;
+    __syncthreads();
+    BatchHeader* hdr = A.hdr;
+    uint32_t consumed = __ldcg(&hdr->consumed);
+    uint32_t nl_kept = total_nl;
+    if (FMT == SBR_FMT_FASTA) {
+        if (A.final_batch) consumed = A.nbytes;
+        else {  // the last record start of a non-final batch opens an incomplete record
+            total_rec -= 1;  // there is always record 0
+            const uint4 L = __ldcg(reinterpret_cast<const uint4*>(A.info + sc[17]) + 1);  // {last_start_nl, last_start_off, -, -}
+            consumed = L.x ? L.y : 0u;  // record 0 itself when no other start exists
+            nl_kept = sc[18] + L.x;
+        }
+    }
+    const bool fail = sc[16] != 0u || total_rec > A.max_records;
+    if (fail)  // rare: the exact scan's tile descriptors must start out zeroed (the launch path does not memset them)
+        for (uint32_t i = tid; i < A.n_desc; i += FAST_THREADS) A.lookback_desc[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) {
+        A.region_base[n_regions] = total_rec;
+        if (A.stats) atomicAdd(&A.stats[fail ? 1 : 0], 1u);
+        if (fail) {  // hand the batch to the exact scan with a clean header
+            hdr->spec_fail = 1;
+            hdr->mode = 0;
+            hdr->status = 0;
+            hdr->first_bad_inv = 0;
+            hdr->n_records = 0;
+            hdr->consumed = 0;
+        } else {
+            hdr->mode = 1;
+            hdr->n_regions = n_regions;
+            hdr->n_records = total_rec;
+            hdr->total_records = total_rec;
+            hdr->n_units = FMT == SBR_FMT_FASTQ ? total_nl : total_rec + (A.final_batch ? 0u : 1u);
+            hdr->fmt = FMT;
+            hdr->consumed = consumed;
+            hdr->nl_total = total_nl;
+            A.rec_off_dense[total_rec] = consumed;
+            if (FMT == SBR_FMT_FASTA && nl_kept != 2u * total_rec) atomicOr(&hdr->status, SBR_ST_NONCANONICAL);
+        }
+    }
+}
+
+// KW: 32-bit words of text covering the match window (ceil(bc_len / 4), 1..4) in packed mode; 0 = unpacked keys.
+// Register cap: 48 per thread costs no spills and no extra instructions over the 60 ptxas takes when left alone, and
+// leaves a quarter of the register file to the previous batch's match + partition kernel, which runs beside the scan
+// (4 scan CTAs + 1 match CTA per SM, see ctx.cu).
+#ifndef SBR_SCAN_NREG
+#define SBR_SCAN_NREG 48
+#endif
 template <int FMT, int KW>
-__global__ void __launch_bounds__(FAST_THREADS, 4) k_scan_fast(FastArgs A) {
+__global__ void __maxnreg__(SBR_SCAN_NREG) k_scan_fast(FastArgs A) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     constexpr int STAGE_STRIDE = stage_stride(FMT);
     uint8_t* stage_buf = dyn_smem + (STAGE_STRIDE - FAST_TILE);  // stage s = stage_buf + s * STAGE_STRIDE, its tail pad right before it
@@ -214,13 +330,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_scan_fast(FastArgs A) {
     // A.ntiles / tiles_per_region count FAST_TILE-sized tiles
     const uint32_t t_lo = c * A.tiles_per_region + min(c, A.extra_regions);
     const uint32_t t_hi = min(t_lo + A.tiles_per_region + (c < A.extra_regions ? 1u : 0u), A.ntiles);
-    if (t_lo >= A.ntiles) {
-        if (tid == 0) {
-            RegionInfo e = {0u, 0u, PHASE_UNKNOWN, 0u, 0u, 0u, {0u, 0u}};
-            A.info[c] = e;
-        }
-        return;
-    }
+    const bool idle = t_lo >= A.ntiles;  // (scan_fast_regions() hands every CTA at least one tile; kept for safety)
     const uint32_t region_lo = t_lo * (uint32_t)FAST_TILE;
     const uint32_t region_hi = min(t_hi * (uint32_t)FAST_TILE, A.nbytes);
     const uint32_t c7f = A.c7f, c0a = A.c0a, c80 = A.c80;
@@ -267,7 +377,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_scan_fast(FastArgs A) {
     uint32_t* const seg_off_c = A.seg_rec_off + (size_t)c * A.cap_r;
     uint64_t* const seg_key_c = A.seg_key + (size_t)c * A.cap_r;
     __syncthreads();
-    if (tid == 0)
+    if (tid == 0 && !idle)
         for (int s = 0; s < FAST_STAGES; ++s)
             if (t_lo + s < t_hi) issue(s, t_lo + s);
 
@@ -280,7 +390,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_scan_fast(FastArgs A) {
     // more barrier and on-demand loads.
     for (uint32_t it = 0;; ++it) {
         const uint32_t tile = t_lo + it;
-        if (tile >= A.ntiles) break;
+        if (idle || tile >= A.ntiles) break;
         const bool overrun = tile >= t_hi;
         if (overrun) {
             if (FMT == SBR_FMT_FASTA) break;
@@ -583,7 +693,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_scan_fast(FastArgs A) {
                         // all A/C/G/T: no line end can hide in the window.  Otherwise (an N, say) the window must be
                         // known to lie on the first sequence line: the next newline is listed and far enough
                         if ((key >> 32) == 0) why = 0;
-                        else {
+                        else if (lds_u8(sbase + hend + 1) != '>') {  // ('>' right behind the header: an empty record, the general path's case)
                             // (+1: the line may end in CR LF, and the CR must stay outside the window too)
                             const uint32_t e2 = ahead(idx + 2);
                             if (e2 != NOPOS && e2 > hend + A.bc_len + 1) why = 0;
@@ -626,7 +736,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_scan_fast(FastArgs A) {
     __syncthreads();
 
     if (tid == 0) {
-        const uint32_t n_it = t_hi - t_lo;  // own tiles processed: the final counts sit in parity n_it & 1
+        const uint32_t n_it = idle ? 0u : t_hi - t_lo;  // own tiles processed: the final counts sit in parity n_it & 1
         RegionInfo e;
         e.nl_own = S.nl_own;
         uint32_t nrec = 0, last_end = 0;
@@ -642,86 +752,15 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_scan_fast(FastArgs A) {
         A.info[c] = e;
         if (last_end) atomicMax(&A.hdr->consumed, last_end);
         if (S.crlf) atomicOr(&A.hdr->status, SBR_ST_NONCANONICAL);
+        // the ticket: everything this CTA wrote (the barrier above ordered its other threads' stores and atomics
+        // before this fence) is visible to whoever draws the last number
+        __threadfence();
+        S.is_last = atomicAdd(&A.hdr->arrive, 1u) == gridDim.x - 1u ? 1u : 0u;
     }
-}
-
-// Verifies the regions against exact prefix sums and publishes the batch header (one block).
-template <int FMT>
-__global__ void __launch_bounds__(MAX_REGIONS) k_scan_finish(BatchHeader* hdr, RegionInfo* info, uint32_t n_regions,
-                                                            uint32_t nbytes, uint32_t max_records, uint32_t final_batch,
-                                                            uint32_t* region_base /* [n_regions+1] */,
-                                                            uint32_t* rec_off_dense, uint4* lookback_desc,
-                                                            uint32_t n_desc) {
-    __shared__ uint32_t s_nl[MAX_REGIONS], s_rec[MAX_REGIONS];
-    __shared__ uint32_t s_fail, s_last_region;
-    const uint32_t c = threadIdx.x;
-    RegionInfo e = {0u, 0u, PHASE_UNKNOWN, 0u, 0u, 0u, {0u, 0u}};
-    if (c < n_regions) e = info[c];
-    s_nl[c] = e.nl_own;
-    s_rec[c] = e.nrec;
-    if (c == 0) { s_fail = 0; s_last_region = 0; }
     __syncthreads();
-    // exclusive prefix sums by a simple Hillis-Steele pass (n_regions <= 1024)
-    for (uint32_t d = 1; d < MAX_REGIONS; d <<= 1) {
-        uint32_t a = c >= d ? s_nl[c - d] : 0u, b = c >= d ? s_rec[c - d] : 0u;
-        __syncthreads();
-        s_nl[c] += a;
-        s_rec[c] += b;
-        __syncthreads();
-    }
-    const uint32_t nl_before = s_nl[c] - e.nl_own, rec_before = s_rec[c] - e.nrec;
-    const uint32_t total_nl = s_nl[MAX_REGIONS - 1];
-    uint32_t total_rec = s_rec[MAX_REGIONS - 1];
-    bool bad = false;
-    if (c < n_regions) {
-        if (e.flags & 1u) bad = true;
-        if (FMT == SBR_FMT_FASTQ) {
-            if (e.phase == PHASE_UNKNOWN) bad |= e.nl_own != 0;          // lines it could not place
-            else bad |= e.phase != (nl_before & 3u);                     // detected phase vs the exact one
-        }
-        if (e.nrec) atomicMax(&s_last_region, c);
-    }
-    if (bad) s_fail = 1;
-    __syncthreads();
-    uint32_t consumed = hdr->consumed;
-    uint32_t nl_kept = total_nl;
-    if (FMT == SBR_FMT_FASTA) {
-        if (final_batch) consumed = nbytes;
-        else {  // the last record start of a non-final batch opens an incomplete record
-            total_rec -= 1;  // there is always record 0
-            const RegionInfo& L = info[s_last_region];
-            consumed = L.last_start_nl ? L.last_start_off : 0u;  // record 0 itself when no other start exists
-            nl_kept = (s_nl[s_last_region] - info[s_last_region].nl_own) + L.last_start_nl;
-        }
-    }
-    if (total_rec > max_records) s_fail = 1;
-    __syncthreads();
-    const bool fail = s_fail != 0;
-    if (fail)  // rare: the exact scan's tile descriptors must start out zeroed (the launch path no longer memsets them)
-        for (uint32_t i = c; i < n_desc; i += MAX_REGIONS) lookback_desc[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (c < n_regions) region_base[c] = rec_before;
-    if (c == 0) {
-        region_base[n_regions] = total_rec;
-        if (fail) {  // hand the batch to the exact scan with a clean header
-            hdr->spec_fail = 1;
-            hdr->mode = 0;
-            hdr->status = 0;
-            hdr->first_bad_inv = 0;
-            hdr->n_records = 0;
-            hdr->consumed = 0;
-        } else {
-            hdr->mode = 1;
-            hdr->n_regions = n_regions;
-            hdr->n_records = total_rec;
-            hdr->total_records = total_rec;
-            hdr->n_units = FMT == SBR_FMT_FASTQ ? total_nl : total_rec + (final_batch ? 0u : 1u);
-            hdr->fmt = FMT;
-            hdr->consumed = consumed;
-            hdr->nl_total = total_nl;
-            rec_off_dense[total_rec] = consumed;
-            if (FMT == SBR_FMT_FASTA && nl_kept != 2u * total_rec) atomicOr(&hdr->status, SBR_ST_NONCANONICAL);
-        }
-    }
+    if (!S.is_last) return;
+    __threadfence();
+    scan_finish<FMT>(A, gridDim.x, reinterpret_cast<uint32_t*>(dyn_smem));  // the stage is free: scratch
 }
 
 }  // namespace
@@ -787,7 +826,7 @@ cudaError_t scan_fast_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbyte
                              uint32_t packed,
                              uint32_t final_batch, BatchHeader* hdr, RegionInfo* info, uint32_t* region_base,
                              uint32_t* seg_rec_off, uint64_t* seg_key, uint32_t* rec_off_dense, uint4* lookback_desc,
-                             uint32_t n_desc, cudaStream_t stream) {
+                             uint32_t n_desc, uint32_t* stats, cudaStream_t stream) {
     FastArgs A;
     A.text = d_text;
     A.nbytes = nbytes;
@@ -808,16 +847,15 @@ cudaError_t scan_fast_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbyte
     A.info = info;
     A.seg_rec_off = seg_rec_off;
     A.seg_key = seg_key;
+    A.max_records = max_records;
+    A.n_desc = n_desc;
+    A.region_base = region_base;
+    A.rec_off_dense = rec_off_dense;
+    A.lookback_desc = lookback_desc;
+    A.stats = stats;
     size_t smem = scan_fast_smem_bytes(fmt);
-    if (fmt == SBR_FMT_FASTQ) {
-        fast_kernel<SBR_FMT_FASTQ>(bc_len, packed)<<<n_regions, FAST_THREADS, smem, stream>>>(A);
-        k_scan_finish<SBR_FMT_FASTQ><<<1, MAX_REGIONS, 0, stream>>>(hdr, info, n_regions, nbytes, max_records, final_batch,
-                                                                    region_base, rec_off_dense, lookback_desc, n_desc);
-    } else {
-        fast_kernel<SBR_FMT_FASTA>(bc_len, packed)<<<n_regions, FAST_THREADS, smem, stream>>>(A);
-        k_scan_finish<SBR_FMT_FASTA><<<1, MAX_REGIONS, 0, stream>>>(hdr, info, n_regions, nbytes, max_records, final_batch,
-                                                                    region_base, rec_off_dense, lookback_desc, n_desc);
-    }
+    if (fmt == SBR_FMT_FASTQ) fast_kernel<SBR_FMT_FASTQ>(bc_len, packed)<<<n_regions, FAST_THREADS, smem, stream>>>(A);
+    else fast_kernel<SBR_FMT_FASTA>(bc_len, packed)<<<n_regions, FAST_THREADS, smem, stream>>>(A);
     return cudaGetLastError();
 }
 

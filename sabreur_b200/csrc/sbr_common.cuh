@@ -42,7 +42,7 @@ struct BatchHeader {
     uint32_t spec_fail;      // fast scan gave up: the look-back scan must run
     uint32_t consumed;       // fast scan: end of the last complete record
     uint32_t n_regions;
-    uint32_t pad[1];
+    uint32_t arrive;         // fast scan: CTAs that have finished their region (the last one runs the epilogue)
 };
 static_assert(sizeof(BatchHeader) == 64, "BatchHeader is one 64-byte line");
 

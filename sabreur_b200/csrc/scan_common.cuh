@@ -85,6 +85,10 @@ __device__ __forceinline__ uint32_t fasta_eval(const ByteSrc& B, uint32_t nbytes
         while (h < nbytes && B(h) != '\n') ++h;
     }
     uint32_t q = h + 1, got = 0, codes = 0, inval = 0, first_seq = NOPOS, why = 2;
+    if (k && q < nbytes && B(q) == '>') {  // the next record starts right behind the header: an empty sequence
+        key = KEY_SHORT | (packed ? 0ull : (uint64_t)q);
+        return 1;
+    }
     while (got < k) {
         if (q >= nbytes) break;
         uint32_t c = B(q);

@@ -142,6 +142,16 @@ class Demux:
     def demux_device(self, slot: int, d_ptr: int, nbytes: int, final: bool = True, stream: int = 0):
         self._check(self.lib.sbr_demux_device(self.h, slot, d_ptr, nbytes, int(final), stream), "sbr_demux_device")
 
+    def join(self, stream: int = 0):
+        """CFG_OVERLAP: `stream` waits for the match + partition work outstanding on the slots' own streams"""
+        self._check(self.lib.sbr_device_join(self.h, stream), "sbr_device_join")
+
+    def scan_stats(self, reset: bool = False) -> tuple[int, int]:
+        """(batches the region-parallel scan finished, batches it handed over to the exact scan)"""
+        out = (C.c_uint64 * 2)()
+        self._check(self.lib.sbr_scan_stats(self.h, C.byref(out), int(reset)), "sbr_scan_stats")
+        return int(out[0]), int(out[1])
+
     def lut(self) -> np.ndarray | None:
         n = self.lib.sbr_lut_entries(self.h)
         if n == 0:

@@ -102,7 +102,7 @@ def make_case(seed: int):
         a, e = starts[j], (starts[j + 1] if j + 1 < i else len(text))
         rec = text[a:e]
         lines = rec.split(b"\n")
-        kind = rng.choice(("start", "sep", "unequal", "short", "trunc") if fastq else ("short", "short_last"))
+        kind = rng.choice(("start", "sep", "unequal", "short", "trunc") if fastq else ("short", "short_last", "empty", "empty"))
         if kind == "start":
             rec = b"X" + rec[1:]
         elif kind == "sep":
@@ -114,6 +114,8 @@ def make_case(seed: int):
             rec = b"\n".join(lines)
         elif kind == "short":
             rec = (b"@s\n" + b"A" * (k - 1) + b"\n+\n" + b"I" * (k - 1) + b"\n") if fastq else (b">s\n" + b"A" * (k - 1) + b"\n")
+        elif kind == "empty":  # header directly followed by the next record's '>' (or by a blank line)
+            rec = lines[0] + b"\n" + rng.choice((b"", b"", b"\n", b"\r\n"))
         elif kind == "short_last":
             a = e = len(text)
             starts.append(a)

@@ -24,7 +24,7 @@ def test_header_symbols_are_exported(lib):
     assert declared == set(_ffi.EXPORTS), declared ^ set(_ffi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/sabreur_gpu.h but not exported"
-    assert lib.sbr_abi_version() == 1
+    assert lib.sbr_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu(lib):

@@ -120,6 +120,88 @@ def test_device_resident_batch_equals_oracle(gpu):
     assert np.array_equal(b.rec_off[:-1].astype(np.uint64), exp["recs"]["rec_off"])
 
 
+@pytest.mark.parametrize("name,n,nb", [("cfg3", 30_000, 7), ("cfg4", 20_000, 5), ("cfg5", 25_000, 6)])
+@pytest.mark.parametrize("extra", [0, 0x10])  # fused cooperative launch / separate launches
+def test_overlapped_pipeline_equals_oracle(gpu, name, n, nb, extra):
+    """SBR_CFG_OVERLAP (the benchmark's HBM-resident loop): batches are launched back to back on one stream and rotate
+    through three device workspaces; match + partition of a batch run on the slot's own stream beside the next scan.
+    Every batch must come out exactly as the oracle's, whatever ran concurrently."""
+    torch, synth, dmx, ffi = gpu["torch"], gpu["synth"], gpu["demux"], gpu["ffi"]
+    w = synth.WORKLOADS[name]
+    tab = synth.table(w)
+    bcs = [bytes(r) for r in tab]
+    rec = w.rec_bytes
+    dev = torch.empty(n * nb * rec + 64, dtype=torch.uint8, device="cuda")
+    synth.reads_device(w, tab, 5_000_000, n * nb, dev.data_ptr())
+    host = dev[: n * nb * rec].cpu().numpy()
+    st = torch.cuda.Stream()
+    S = 3
+    with dmx.Demux(bcs, w.mismatch, fmt=w.fmt, batch_bytes=n * rec + 4096, n_slots=S, max_records=n + 16,
+                   flags=ffi.CFG_OVERLAP | ffi.CFG_TIMING | extra) as dm:
+        for rnd in range(2):  # the second round reuses every slot without a host-side wait in between
+            for i in range(nb):
+                dm.demux_device(i % S, dev.data_ptr() + i * n * rec, n * rec, final=True, stream=st.cuda_stream)
+        dm.join(st.cuda_stream)
+        st.synchronize()
+        assert dm.scan_stats() == (2 * nb, 0)
+        for i in range(nb - S, nb):  # the slots hold the last three batches
+            b = dm.wait(i % S)
+            exp = orc.demux(host[i * n * rec:(i + 1) * n * rec], bcs, w.mismatch)
+            assert b.n_records == n and b.status == 0 and b.scan_path == 1 and b.consumed == n * rec
+            assert np.array_equal(b.assign, exp["assign"])
+            assert np.array_equal(b.bin_count, exp["bin_count"]) and np.array_equal(b.bin_start, exp["bin_start"])
+            assert np.array_equal(b.order, exp["order"])
+            assert np.array_equal(b.rec_off[:-1].astype(np.uint64), exp["recs"]["rec_off"])
+        ms, nbatches, launches = dm.timing()
+        assert nbatches == 2 * nb and all(t > 0 for t in ms[:2])
+        # one at a time as well (submit, wait, submit ...), every batch checked
+        for i in range(nb):
+            dm.demux_device(i % S, dev.data_ptr() + i * n * rec, n * rec, final=True, stream=st.cuda_stream)
+            b = dm.wait(i % S)
+            exp = orc.demux(host[i * n * rec:(i + 1) * n * rec], bcs, w.mismatch)
+            assert np.array_equal(b.assign, exp["assign"]) and np.array_equal(b.order, exp["order"])
+
+
+def test_scan_stats_count_handed_over_batches(gpu):
+    """the device-side counters bench.py reads: a malformed batch is handed to the exact scan and counted"""
+    torch, dmx, ffi = gpu["torch"], gpu["demux"], gpu["ffi"]
+    recs = [b"@r%d\nACGTACGTAC\n+\nIIIIIIIIII\n" % i for i in range(5000)]
+    good = b"".join(recs)
+    bad = b"".join(recs[:1000]) + b"@x\nACGT\n+\nIII\n" + b"".join(recs[1000:])
+    bcs = [b"ACGT", b"TTTT"]
+    with dmx.Demux(bcs, 0, fmt=2, batch_bytes=1 << 20) as dm:
+        for text, fails in ((good, 0), (bad, 1)):
+            t = torch.frombuffer(bytearray(text + b"\0" * 64), dtype=torch.uint8).cuda()
+            dm.scan_stats(True)
+            dm.demux_device(0, t.data_ptr(), len(text), final=True)
+            fin, handed = dm.scan_stats()
+            assert (fin, handed) == (1 - fails, fails)
+            b = dm.wait(0)
+            assert b.scan_path == (0 if fails else 1)
+            assert bool(b.status & ffi.ST_ERROR_MASK) == bool(fails)
+
+
+def test_missing_final_newline_ships_every_scan_word(gpu):
+    """when only the host knows that the batch is non-canonical (it supplied the stream's final newline),
+    rec_key must still hold the scan word of EVERY record, not just the patched last one"""
+    dmx, ffi = gpu["demux"], gpu["ffi"]
+    recs = [(b"r%d" % i, bytes(b"ACGT"[(i >> (2 * j)) & 3] for j in range(10))) for i in range(3000)]
+    text = b"".join(b"@" + h + b"\n" + s + b"\n+\n" + b"I" * 10 + b"\n" for h, s in recs)[:-1]
+    bcs = [b"ACGTAC", b"TTTTTT"]
+    with dmx.Demux(bcs, 0, batch_bytes=1 << 20) as dm:
+        buf = dm.slot_buffer(0)
+        buf[:len(text)] = np.frombuffer(text, dtype=np.uint8)
+        dm.submit(0, 0, len(text), 0, True)
+        b = dm.wait(0)
+    assert b.n_records == len(recs) and b.status & ffi.ST_NONCANONICAL and b.rec_key is not None
+    code = {65: 0, 67: 1, 84: 2, 71: 3}
+    for i in (0, 1, 17, 1500, len(recs) - 2, len(recs) - 1):
+        want = sum(code[c] << (2 * j) for j, c in enumerate(recs[i][1][:6]))
+        assert int(b.rec_key[i]) & 0xFFF == want, i
+        assert bool(int(b.rec_key[i]) & ffi.KEY_NONCANON) == (i == len(recs) - 1)
+    assert b.consumed == len(text)
+
+
 # ---- the in-tree fixtures (SURVEY 8c goldens) -------------------------------------------------------
 R1_GOLD = ["90d9764b8b69432c", "dd06fd51837741d1", "98a7be33c3ac7170", "5af261ae384d0e8d", "cf6171f02f1974ce",
            "8a8208327d1ba4cc", "d88301f0531c93a4", "9e490c81cc82b11e", "88d17addc88d6666", "5a32eafb431d020f"]
@@ -251,17 +333,43 @@ def test_ragged_and_non_acgt_tables(gpu):
     (b"@a\nACGT\n+\nIIII\n\n\n\n\n", "start"),
     (b"ACGT\n", "start"),
     (b">a\nAC\n>b\nACGT\n", "short"),
+    (b">a\n>b\nACGT\n", "short"),              # an empty sequence: the next record starts right behind the header
+    (b">x\nACGT\n>a\n>bbbbbbbbbbbbbbbbbb\nACGTACGT\n>c\nACGT\n", "short"),
+    (b">a\n\n>b\nACGT\n", "short"),
 ])
 def test_parse_violations_are_reported_like_the_oracle(gpu, text, code):
     ffi, dm = gpu["ffi"], gpu["demux"]
     bits = {"unequal": ffi.ST_UNEQUAL_LEN, "sep": ffi.ST_INVALID_SEP, "start": ffi.ST_INVALID_START,
             "short": ffi.ST_SHORT_READ, "trunc": ffi.ST_TRUNCATED}[code]
-    got = dm.demux_bytes(text, [b"ACGT", b"TTTT"], 0, batch_bytes=1 << 16)
-    assert got["bad"] is not None and got["bad"][1] & bits
     with pytest.raises(orc.OracleError) as e:
         orc.demux(text, [b"ACGT", b"TTTT"], 0)
-    if code != "start" or text[:1] in b"@>":
-        assert got["bad"][0] == e.value.record
+    for flags in (0, ffi.CFG_EXACT_SCAN, ffi.CFG_GENERIC):
+        got = dm.demux_bytes(text, [b"ACGT", b"TTTT"], 0, batch_bytes=1 << 16, flags=flags)
+        assert got["bad"] is not None and got["bad"][1] & bits
+        if code != "start" or text[:1] in b"@>":
+            assert got["bad"][0] == e.value.record
+
+
+def test_fasta_empty_sequences_inside_a_large_batch(gpu):
+    """records whose header is directly followed by the next '>' (ADVICE r1): a short read at exactly that record,
+    wherever it falls in a region / slice of the region-parallel scan"""
+    rng = random.Random(5)
+    ffi, dm = gpu["ffi"], gpu["demux"]
+    bcs = [bytes(rng.choice(b"ACGT") for _ in range(6)) for _ in range(12)]
+    for bad_at in (1, 777, 20011, 39998):
+        out = bytearray()
+        for i in range(40000):
+            L = rng.randint(20, 70)
+            out += b">r%d\n" % i
+            if i != bad_at:
+                out += bytes(rng.choice(b"ACGT") for _ in range(L)) + b"\n"
+        text = bytes(out)
+        with pytest.raises(orc.OracleError) as e:
+            orc.demux(text, bcs, 1)
+        assert e.value.record == bad_at
+        for flags in (0, ffi.CFG_EXACT_SCAN):
+            got = dm.demux_bytes(text, bcs, 1, batch_bytes=4 << 20, flags=flags)
+            assert got["bad"] == (bad_at, ffi.ST_SHORT_READ)
 
 
 def test_adversarial_phase_detection(gpu):

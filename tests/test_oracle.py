@@ -202,3 +202,23 @@ def test_ragged_barcode_lengths():
     text = b">a\nACGTAAAA\n>b\nACCCAAAA\n"
     d = orc.demux(text, [b"TTTT", b"ACGTAC", b"AC"], 0)
     assert d["assign"].tolist() == [1, 2]
+
+
+# --- the oracle-side synthetic generator (oracle/synth_ref.c) against the product's ------------
+@pytest.mark.parametrize("name", ["cfg3", "cfg4", "cfg5"])
+def test_synth_ref_equals_product_generator(name):
+    """bench.py --impl reference builds its input with the oracle's restatement of the generator (so that the process
+    timing the CPU baseline never maps libsabreur_gpu.so); it must be the same workload byte for byte.  sbr_synth_host
+    and sbr_synth_table are plain host functions: no GPU is needed."""
+    from sabreur_b200 import synth
+    w = synth.WORKLOADS[name]
+    tab = synth.table(w)
+    ref_tab = orc.synth_table(w.cfg_id, w.n_barcodes, w.bc_len, w.min_dist)
+    assert np.array_equal(tab, ref_tab)
+    seed = synth.SEED_READS + w.cfg_id
+    for mate in ((0, 1) if w.paired else (0,)):
+        for first, n in ((0, 3000), (999_999_999_000, 700)):
+            want = synth.reads_host(w, tab, first, n, mate)
+            got = orc.synth_reads(w.fmt, w.read_len, mate, seed, ref_tab, first, n, threads=3 if first == 0 else 1)
+            assert got.size == n * w.rec_bytes
+            assert np.array_equal(got, want)

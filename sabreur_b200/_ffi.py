@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsabreur_gpu.so")
+LIB_PATH = os.environ.get("SABREUR_GPU_LIB") or os.path.join(HERE, "lib", "libsabreur_gpu.so")  # (the override: experimental builds)
 
 SBR_OK = 0
 ST_INVALID_START, ST_INVALID_SEP, ST_UNEQUAL_LEN, ST_SHORT_READ = 0x01, 0x02, 0x04, 0x08

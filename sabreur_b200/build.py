@@ -29,7 +29,13 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines: list[str] | None = None) -> str:
+    """variant: an experimental build with extra -D flags, kept apart in lib_<variant>/ (select it at run time with
+    SABREUR_GPU_LIB=<path>); the product is the plain build in lib/"""
+    global LIBDIR, LIB
+    if variant:
+        LIBDIR = os.path.join(HERE, "lib_" + variant)
+        LIB = os.path.join(LIBDIR, "libsabreur_gpu.so")
     os.makedirs(LIBDIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "sabreur_gpu.h"))
@@ -41,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(LIBDIR, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + list(defines or []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()
@@ -56,4 +62,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    var = ""
+    if "--variant" in sys.argv:
+        var = sys.argv[sys.argv.index("--variant") + 1]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var,
+                defines=[a for a in sys.argv[1:] if a.startswith("-D")]))

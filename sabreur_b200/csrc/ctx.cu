@@ -42,7 +42,7 @@ struct MatchLaunch {
     uint32_t force_keys;
 };
 size_t match_smem(uint32_t n, uint32_t stride, uint32_t nbins, bool generic);
-cudaError_t match_prepare();
+cudaError_t match_prepare(bool max_shared);
 int match_fused_max_grid(int device, int mode, size_t smem);
 cudaError_t match_build_lut(const uint2* d_tab, uint32_t n, uint32_t m, uint32_t k, uint16_t* d_lut, cudaStream_t stream);
 cudaError_t match_launch(const MatchLaunch& L, cudaStream_t stream);
@@ -54,7 +54,7 @@ struct PartitionPlan {
     uint32_t nbits;
 };
 PartitionPlan partition_plan(uint32_t nbins, uint32_t max_records, int sms);
-cudaError_t partition_prepare();
+cudaError_t partition_prepare(bool max_shared);
 cudaError_t partition_launch(const uint16_t* d_assign, const BatchHeader* d_hdr, uint32_t nbins,
                              uint32_t* d_cta_cnt, uint32_t* d_bin_count, uint32_t* d_bin_start, uint32_t* d_order,
                              uint32_t* d_done_counter, BatchHeader* d_zero_next, const PartitionPlan& p, cudaStream_t stream);
@@ -262,8 +262,6 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
     CU(c, scan_prepare(cfg->device, &c->scan_grid));
     CU(c, scan_fast_prepare(cfg->device, &c->fast_grid_q, &c->fast_grid_a));
     c->exact_only = (cfg->flags & SBR_CFG_EXACT_SCAN) != 0;
-    CU(c, match_prepare());
-    CU(c, partition_prepare());
     c->plan = partition_plan(c->nbins, c->max_records, c->sms);
     if (match_smem(n, k, c->nbins, !c->packed) > 200 * 1024) return fail(c, SBR_E_UNSUPPORTED, "barcode table too large");
     const bool will_lut = c->packed && !(cfg->flags & SBR_CFG_NO_LUT) && k <= 12;
@@ -278,6 +276,10 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
         const size_t need = 4 * (scan_smem + 1024) + match_smem(n, k, c->nbins, !c->packed) + 1024;
         if (need > 228 * 1024 && !getenv("SBR_OVERLAP_FORCE")) c->overlap = false;
     }
+    // (function attributes are process-wide: each context sets the split it needs, the last one created wins -- contexts of
+    // both kinds in one process still run correctly, the loser just has the slower split)
+    CU(c, match_prepare(c->overlap));
+    CU(c, partition_prepare(c->overlap));
     if (c->overlap) {
         // match + partition of batch i run beside the scan of batch i+1: the scan holds 4 CTAs x 256 threads x 48
         // registers and ~47 KB of shared memory each on every SM, which leaves room for exactly one 256-thread CTA of

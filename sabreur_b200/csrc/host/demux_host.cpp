@@ -24,6 +24,8 @@
 #include <mutex>
 #include <thread>
 
+#include <unistd.h>
+
 #include "../../../include/sabreur_gpu.h"
 
 namespace sabreur {
@@ -196,8 +198,8 @@ void give_pooled(const std::vector<uint8_t>& key, const std::vector<Gpu>& gpus);
 class Pass {
 public:
     Pass(const std::string& path, std::vector<FILE*> bin_files, const std::vector<std::string>& barcodes, uint8_t mismatch,
-         Format out_format, int level, const HostOptions& opt, RunStats* stats)
-        : path_(path), opt_(opt), out_format_(out_format), level_(level), stats_(stats) {
+         Format out_format, int level, const HostOptions& opt, RunStats* stats, const std::atomic<bool>* cancel = nullptr)
+        : path_(path), opt_(opt), out_format_(out_format), level_(level), stats_(stats), cancel_(cancel) {
         n_bins_ = (uint32_t)barcodes.size() + 1;
         sinks_.resize(n_bins_);
         for (uint32_t b = 0; b < n_bins_; ++b) sinks_[b].fh = bin_files[b];
@@ -302,6 +304,7 @@ private:
             uint32_t fmt = 0;
             bool eof = false;
             while (!eof && !stop_.load()) {
+                if (cancelled()) { stop_after_error(); break; }
                 {   // slot of batch `seq` is free once batch seq - G*S has been written
                     std::unique_lock<std::mutex> l(slot_m_);
                     slot_cv_.wait(l, [&] { return stop_.load() || written_ + (uint64_t)G_ * S_ > seq; });
@@ -347,7 +350,10 @@ private:
                     else { peeked_ = true; peek_byte_ = probe; }
                 }
                 uint64_t n = fill - b.off;
-                if (seq == 0 && n == 0) { bad_flags_ = SBR_ST_INVALID_START; bad_record_ = 0; break; }  // empty input: needletail refuses it
+                // needletail::parse_fastx_reader(..)? (demux.rs:23, 85-86) fails before any record is read when the stream
+                // is empty or starts with neither '>' nor '@': an error in single-end AND paired-end mode
+                if (seq == 0 && n == 0) throw ParseError("record 0: empty input");
+                if (seq == 0 && buf[b.off] != '>' && buf[b.off] != '@') throw ParseError("record 0: invalid start byte");
                 carry.clear();
                 if (!eof) {
                     uint64_t cut = guess_cut(buf + b.off, n, fmt, std::min<uint64_t>(spill.empty() ? reserve_ : reserve_ / 2, 1ull << 20));
@@ -399,6 +405,7 @@ private:
         std::deque<Batch> flight;
         bool input_done = false;
         while (!stop_.load()) {
+            if (cancelled()) { stop_after_error(); break; }
             Batch nb;
             // keep every slot busy: take whatever the reader has ready
             while (!input_done && flight.size() < (size_t)G_ * S_ && filled_.try_pop(nb)) {
@@ -460,6 +467,7 @@ private:
         stop_.store(true);
         slot_cv_.notify_all();
     }
+    bool cancelled() const { return cancel_ && cancel_->load(); }
     void run_extra() {  // rare: the last batch hit the record capacity; its rest is processed after the writer released the slot
         pending_extra_ = false;
         while (!prefix_.empty()) {
@@ -582,6 +590,7 @@ private:
     Format out_format_;
     int level_;
     RunStats* stats_;
+    const std::atomic<bool>* cancel_ = nullptr;  // paired-end: the other mate's pass failed, stop quietly
     uint32_t n_bins_ = 0;
     int G_ = 1;
     uint32_t S_ = 2;
@@ -625,6 +634,13 @@ void give_pooled(const std::vector<uint8_t>& key, const std::vector<Gpu>& gpus) 
     g_pool_key = key;
 }
 
+void truncate_file(FILE* fh) {
+    if (!fh) return;
+    fflush(fh);
+    if (ftruncate(fileno(fh), 0) != 0) throw std::runtime_error("ftruncate failed");
+    rewind(fh);
+}
+
 std::vector<std::string> barcode_list(const Barcode& bd) {
     if (bd.rows.empty()) throw std::runtime_error("Barcode data is empty");  // demux.rs:31-33
     std::vector<std::string> v;
@@ -665,25 +681,43 @@ std::pair<Counts&, std::string> pe_demux(const std::string& forward, const std::
     // The reference runs the forward pass, then the reverse pass (demux.rs:101-110, 114-123).  The mates are
     // independent streams writing to disjoint files, so both passes may run at once (each with its own contexts):
     // with compressed inputs the single-threaded inflate of each file is the wall, and two of them run in parallel.
+    // Both parsers are built before the first record is processed (demux.rs:85-86): an empty mate, or one that starts
+    // with neither '>' nor '@', fails the whole call and nothing is written for either mate.
+    for (const std::string* path : {&forward, &reverse}) {
+        Reader probe(*path);
+        uint8_t first = 0;
+        if (probe.read(&first, 1) == 0) throw ParseError(*path + ": empty input");
+        if (first != '>' && first != '@') throw ParseError(*path + ": invalid start byte");
+    }
     bool unk[2] = {true, true};
     Counts counts[2];
     RunStats st[2];
     std::exception_ptr errs[2];
+    std::atomic<bool> cancel_reverse{false};
     auto run_mate = [&](int mate) {
         try {
             std::vector<FILE*> files;
             for (auto& r : bd.rows) files.push_back(r.files.at(mate).fh);
             files.push_back(bd.unknown.at(mate).fh);
-            Pass pass(mate == 0 ? forward : reverse, files, bcs, mismatch, compression, level, opt, stats ? &st[mate] : nullptr);
+            Pass pass(mate == 0 ? forward : reverse, files, bcs, mismatch, compression, level, opt, stats ? &st[mate] : nullptr,
+                      mate == 1 ? &cancel_reverse : nullptr);
             unk[mate] = pass.run(/*strict=*/false, counts[mate], bcs);
         } catch (...) {
             errs[mate] = std::current_exception();
+            if (mate == 0) cancel_reverse.store(true);
         }
     };
     if (opt.parallel_mates) {
         std::thread t1([&] { run_mate(1); });
         run_mate(0);
         t1.join();
+        if (errs[0]) {
+            // The reference reaches the reverse loop only after the forward loop has finished (demux.rs:101-123): when
+            // the forward pass dies (short-read panic, I/O error) the reverse files are still empty.  Here the reverse
+            // pass ran beside it: it has been told to stop, and what it wrote is taken back.
+            for (auto& r : bd.rows) truncate_file(r.files.at(1).fh);
+            truncate_file(bd.unknown.at(1).fh);
+        }
     } else {
         run_mate(0);
         if (!errs[0]) run_mate(1);

@@ -229,6 +229,11 @@ int main(int argc, char** argv) {
         ss << bf.rdbuf();
         const auto fields = split_by_tab(ss.str());
         if (cli.mismatch != 0) WARN("Allowing up to %d mismatches", cli.mismatch);
+        // With three or more mismatches the reference's "XXX" sentinel (demux.rs:37, 43-46) matches every read that reaches
+        // it: such reads land in the unknown file while is_unk_empty stays true, and main.rs:179-181 may then delete that
+        // file with reads in it.  That file-deleting quirk is not reproduced: unknown reads are kept and reported as such.
+        if (cli.mismatch >= 3)
+            WARN("--mismatch >= 3: the reference's 'XXX' sentinel quirk is not emulated, unmatched reads are kept in the unknown file");
 
         Barcode bd;
         Counts stats;

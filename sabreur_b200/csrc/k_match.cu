@@ -421,13 +421,19 @@ static MatchKernel match_kernel(int mode, bool fused) {
     }
 }
 
-cudaError_t match_prepare() {
+// max_shared: the kernels will run beside the record scan (overlapped mode), whose CTAs need the SM's largest
+// shared-memory split: ask for the same one, or the two could not be resident together
+cudaError_t match_prepare(bool max_shared) {
     cudaError_t e;
     for (int mode = 0; mode < 3; ++mode)
-        for (int f = 0; f < 2; ++f)
+        for (int f = 0; f < 2; ++f) {
             if ((e = cudaFuncSetAttribute(match_kernel(mode, f != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) !=
                 cudaSuccess)
                 return e;
+            if ((e = cudaFuncSetAttribute(match_kernel(mode, f != 0), cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          max_shared ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault)) != cudaSuccess)
+                return e;
+        }
     return cudaFuncSetAttribute(k_build_lut, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
 }
 

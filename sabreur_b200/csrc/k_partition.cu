@@ -197,7 +197,11 @@ PartitionPlan partition_plan(uint32_t nbins, uint32_t max_records, int sms) {
     return p;
 }
 
-cudaError_t partition_prepare() {
+cudaError_t partition_prepare(bool max_shared) {
+    cudaError_t e;
+    const int carve = max_shared ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault;  // see match_prepare()
+    if ((e = cudaFuncSetAttribute(k_scatter, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_binscan, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 }
 

@@ -27,6 +27,8 @@
 //   * per record: validate ('+' line, equal lengths, CR, next record's '@'), 2-bit pack the first bc_len
 //     bases, write seg_rec_off / seg_key at the region-local index.  The match kernel compacts the
 //     per-region segments into dense arrays while it reads the keys.
+#include <cstdlib>
+
 #include "scan_common.cuh"
 
 namespace sbr {
@@ -57,7 +59,10 @@ constexpr int FAST_STAGES = SBR_SCAN_SINGLE ? 1 : 2;
 // still addressable in shared memory at (stage base + position - tile start)
 constexpr int TAIL_PAD = 512;
 __host__ __device__ constexpr int stage_stride(int fmt) { return (fmt == SBR_FMT_FASTQ ? TAIL_PAD : 0) + FAST_TILE; }  // FASTA has no use for the pad
-constexpr int WL_CAP = SBR_SCAN_SINGLE ? 284 : 188;  // newline positions per warp slice held in shared memory (>= 16.3-byte lines on average)
+#ifndef SBR_WL_CAP
+#define SBR_WL_CAP (SBR_SCAN_SINGLE ? 284 : 188)
+#endif
+constexpr int WL_CAP = SBR_WL_CAP;  // newline positions per warp slice held in shared memory (>= 16.3-byte lines on average)
 constexpr int CNT_BITS = FAST_UNITS == 2 ? 16 : 10;   // per-unit newline counts of a slice share one word (valid while the slice fits WL_CAP)
 constexpr uint32_t CNT_MASK = (1u << CNT_BITS) - 1u;
 constexpr int FASTA_CHUNKS = (WL_CAP + 31) / 32;
@@ -795,6 +800,11 @@ cudaError_t scan_fast_prepare(int device, int* grid_fastq, int* grid_fasta) {
             if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_fast_smem_bytes(fmt))) !=
                 cudaSuccess)
                 return e;
+            // the SM's whole 228 KB as shared memory: four CTAs of the scan need ~193 KB, and the match kernel of the
+            // previous batch must find room beside them (with the 196 KB split the driver would pick it cannot)
+            int carve = cudaSharedmemCarveoutMaxShared;
+            if (const char* ev = getenv("SBR_SCAN_CARVEOUT")) carve = atoi(ev);
+            if ((e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
             int r = 0;
             if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k, FAST_THREADS, scan_fast_smem_bytes(fmt))) != cudaSuccess)
                 return e;

@@ -348,6 +348,9 @@ def _demux_one(path: str, writers: list, unknown_writer, barcodes: list[bytes], 
                     parts.append(rec)
                 w.write(_member(b"".join(parts), fmt, level))
             if b.status & _ffi.ST_ERROR_MASK:
+                if b.record_base + b.first_bad_record == 0 and (b.first_bad_flags & _ffi.ST_INVALID_START):
+                    # parse_fastx_reader(..)? fails before the loop starts (demux.rs:23, 85-86): SE and PE alike
+                    raise ParseError(b.first_bad_flags, 0)
                 if b.first_bad_flags & _ffi.ST_SHORT_READ:
                     raise ParseError(b.first_bad_flags, b.record_base + b.first_bad_record)  # slice panic, demux.rs:54
                 if strict:
@@ -386,6 +389,10 @@ def pe_demux(forward: str, reverse: str, format: str, level: int, barcode_data: 
     which_format(reverse)
     if format != "":
         compression = format
+    for path in (forward, reverse):  # both parsers are built before the first record is processed (demux.rs:85-86)
+        first = next(_read_chunks(path, 1), b"")
+        if first[:1] not in (b">", b"@"):
+            raise ParseError(_ffi.ST_INVALID_START, 0)
     level = level if level in _LEVELS else 1
     bcs = [k for k in barcode_data if k != b"XXX"]
     unk = barcode_data[b"XXX"]

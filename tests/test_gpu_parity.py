@@ -165,7 +165,8 @@ def test_overlapped_pipeline_equals_oracle(gpu, name, n, nb, extra):
 def test_scan_stats_count_handed_over_batches(gpu):
     """the device-side counters bench.py reads: a malformed batch is handed to the exact scan and counted"""
     torch, dmx, ffi = gpu["torch"], gpu["demux"], gpu["ffi"]
-    recs = [b"@r%d\nACGTACGTAC\n+\nIIIIIIIIII\n" % i for i in range(5000)]
+    seq = b"ACGTACGTAC" * 6  # (lines shorter than ~16 bytes on average are the exact scan's job by design)
+    recs = [b"@r%d\n" % i + seq + b"\n+\n" + b"I" * len(seq) + b"\n" for i in range(5000)]
     good = b"".join(recs)
     bad = b"".join(recs[:1000]) + b"@x\nACGT\n+\nIII\n" + b"".join(recs[1000:])
     bcs = [b"ACGT", b"TTTT"]

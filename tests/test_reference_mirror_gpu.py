@@ -106,6 +106,23 @@ def test_pe_demux_fixture(demux):
         assert hashlib.sha256(_gunzip(f2)).hexdigest()[:16] == R2_GOLD[i]
 
 
+def test_pe_demux_refuses_a_mate_that_is_not_a_sequence_file(demux, tmp_path):
+    """demux.rs:85-86: both parsers are built (`?`) before the first record is processed, so an empty or
+    unrecognisable REVERSE mate fails the call before anything is written -- the C++ host and this mirror agree"""
+    import gzip as gz
+    rows = read_barcode_table("bc_pe_fa.txt")
+    junk = tmp_path / "junk.fa"
+    junk.write_bytes(b"not a sequence file\n")
+    empty = tmp_path / "empty.fa.gz"
+    empty.write_bytes(gz.compress(b""))
+    for bad in (str(junk), str(empty)):
+        for fwd, rev in ((_fx("reads_1.fa.gz"), bad), (bad, _fx("reads_2.fa.gz"))):
+            bc_data = _bc_data(*[r[0].encode() for r in rows], files=2)
+            with pytest.raises(demux.ParseError):
+                demux.pe_demux(fwd, rev, NO, LEVEL_ONE, bc_data, 0, {})
+            assert all(f.tell() == 0 for fs in bc_data.values() for f in fs)
+
+
 # ---- src/utils.rs:177-205: the bc_cmp known-answer tests, asked of the GPU match kernel --------------------------
 def _gpu_bc_cmp(demux, bc: bytes, seq: bytes, mismatch: int, **kw) -> bool:
     """bc_cmp(bc, seq, mismatch) as the hot loop uses it: does a read starting with `seq` go to barcode `bc`?"""

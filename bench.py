@@ -381,9 +381,17 @@ def run_block(env: Env, name: str, units: int, primary: bool) -> dict:
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
 
+    holds = [None] * S   # which batch each device workspace holds
+    seq = [0]            # launches so far: workspaces rotate across steps too (a step's last batch and the next step's first
+                         # one must not land in the same workspace, or the second would wait for the first's match kernel)
+
     def launch(i):
         ti, off, nb = batches[i]
-        dm.demux_device(i % S, texts[ti].data_ptr() + off, nb, final=True, stream=stream)
+        slot = seq[0] % S
+        seq[0] += 1
+        holds[slot] = i
+        dm.demux_device(slot, texts[ti].data_ptr() + off, nb, final=True, stream=stream)
+        return slot
 
     def step():
         for i in range(len(batches)):
@@ -401,8 +409,7 @@ def run_block(env: Env, name: str, units: int, primary: bool) -> dict:
     # ---- warm-up 1: every batch of the step once, each one waited for and checked --------------------------
     unknown = 0
     for i in range(len(batches)):
-        launch(i)
-        unknown += check(i, dm.wait(i % S, copy=False))
+        unknown += check(i, dm.wait(launch(i), copy=False))
     for _ in range(max(0, args.warmup - 1)):
         step()
     dm.join(stream)
@@ -430,9 +437,10 @@ def run_block(env: Env, name: str, units: int, primary: bool) -> dict:
     finished, handed_over = dm.scan_stats()
     # the batches still sitting in the slots are the timed loop's last ones: wait for them and check them as well
     last_checked = 0
-    for i in range(max(0, len(batches) - S), len(batches)):
-        check(i, dm.wait(i % S, copy=False))
-        last_checked += 1
+    for slot in range(S):
+        if holds[slot] is not None:
+            check(holds[slot], dm.wait(slot, copy=False))
+            last_checked += 1
     want_batches = args.steps * len(batches)
     self_check = {"batches": len(batches), "checked_each": ["n_records", "status==0", "scan_path==1", "consumed", "sum(bin_count)"],
                   "timed_batches": want_batches, "scan_finished": finished, "spec_fail": handed_over,

@@ -40,10 +40,11 @@ struct MatchLaunch {
     int grid;
     int fused; uint32_t nbits; uint32_t* bin_count; uint32_t* bin_start; uint32_t* order; BatchHeader* zero_next;
     uint32_t force_keys;
+    uint32_t lean;
 };
-size_t match_smem(uint32_t n, uint32_t stride, uint32_t nbins, bool generic);
+size_t match_smem(uint32_t n, uint32_t stride, uint32_t nbins, bool generic, bool lean);
 cudaError_t match_prepare(bool max_shared);
-int match_fused_max_grid(int device, int mode, size_t smem);
+int match_fused_max_grid(int device, int mode, size_t smem, bool lean);
 cudaError_t match_build_lut(const uint2* d_tab, uint32_t n, uint32_t m, uint32_t k, uint16_t* d_lut, cudaStream_t stream);
 cudaError_t match_launch(const MatchLaunch& L, cudaStream_t stream);
 // k_partition.cu
@@ -145,6 +146,7 @@ struct sbr_ctx {
     PartitionPlan plan{};
     bool fused = false;  // match + partition in one cooperative launch
     bool overlap = false;  // device-resident batches: match + partition on the slot's aux stream, beside the next scan
+    bool lean = false;     // the match kernel's shared-memory diet (16-bit per-warp counters): big tables beside the scan
     uint32_t* d_stats = nullptr;  // {batches the region-parallel scan finished, batches it handed to the exact scan, 0, 0}
     std::vector<Slot> slots;
     std::string err;
@@ -263,7 +265,7 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
     CU(c, scan_fast_prepare(cfg->device, &c->fast_grid_q, &c->fast_grid_a));
     c->exact_only = (cfg->flags & SBR_CFG_EXACT_SCAN) != 0;
     c->plan = partition_plan(c->nbins, c->max_records, c->sms);
-    if (match_smem(n, k, c->nbins, !c->packed) > 200 * 1024) return fail(c, SBR_E_UNSUPPORTED, "barcode table too large");
+    if (match_smem(n, k, c->nbins, !c->packed, false) > 200 * 1024) return fail(c, SBR_E_UNSUPPORTED, "barcode table too large");
     const bool will_lut = c->packed && !(cfg->flags & SBR_CFG_NO_LUT) && k <= 12;
     c->overlap = (cfg->flags & SBR_CFG_OVERLAP) != 0;
     if (c->overlap) {
@@ -273,8 +275,16 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
         size_t scan_smem = 0;
         for (uint32_t f = SBR_FMT_FASTA; f <= SBR_FMT_FASTQ; ++f)
             if (cfg->fmt == SBR_FMT_AUTO || cfg->fmt == f) scan_smem = std::max(scan_smem, scan_fast_smem_bytes(f));
-        const size_t need = 4 * (scan_smem + 1024) + match_smem(n, k, c->nbins, !c->packed) + 1024;
-        if (need > 228 * 1024 && !getenv("SBR_OVERLAP_FORCE")) c->overlap = false;
+        // separate launches (SBR_CFG_NO_FUSE): k_scatter keeps 32-bit per-warp cursors of its own
+        const size_t scatter = (cfg->flags & SBR_CFG_NO_FUSE) ? (size_t)8 * c->nbins * 4u : 0u;
+        auto fits = [&](bool lean) {
+            return 4 * (scan_smem + 1024) + std::max(match_smem(n, k, c->nbins, !c->packed, lean), scatter) + 1024 <= 228 * 1024;
+        };
+        // a warp's slice must stay below 65536 records for the 16-bit counters (one CTA per SM, 8 warps each)
+        const bool lean_ok = c->packed && (uint64_t)c->max_records / ((uint64_t)c->sms * 8u) < 60000u;
+        if (getenv("SBR_FORCE_LEAN") && lean_ok) c->lean = true;          // (tests: the lean kernel on small tables)
+        else if (!fits(false) && lean_ok && fits(true)) c->lean = true;
+        if (!fits(c->lean) && !getenv("SBR_OVERLAP_FORCE")) { c->overlap = false; c->lean = false; }
     }
     // (function attributes are process-wide: each context sets the split it needs, the last one created wins -- contexts of
     // both kinds in one process still run correctly, the loser just has the slower split)
@@ -293,7 +303,7 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
     }
     if (!(cfg->flags & SBR_CFG_NO_FUSE)) {
         // kernel 3 rides in the match kernel's launch when the whole grid can be resident at once
-        const int cap = match_fused_max_grid(cfg->device, !c->packed ? 2 : (will_lut ? 0 : 1), match_smem(n, k, c->nbins, !c->packed));
+        const int cap = match_fused_max_grid(cfg->device, !c->packed ? 2 : (will_lut ? 0 : 1), match_smem(n, k, c->nbins, !c->packed, c->lean), c->lean);
         if (cap >= c->sms) {
             c->fused = true;
             if (c->plan.grid > cap) { c->plan.grid = cap; c->plan.V = (uint32_t)cap * 8u; }
@@ -432,6 +442,7 @@ static int launch_match_partition(sbr_ctx* c, Slot& s, const uint8_t* d_text, ui
     L.bin_count = s.d_bin_count; L.bin_start = s.d_bin_start; L.order = s.d_order;
     L.zero_next = s.d_hdr2 + (s.hdr_idx ^ 1u);
     L.force_keys = s.supplied_nl ? 1u : 0u;  // sbr_wait flags the patched last record: every scan word must be there
+    L.lean = c->lean ? 1u : 0u;
     CU(c, match_launch(L, st));
     if (ev) CU(c, cudaEventRecord(ev[2], st));
     if (!c->fused)

@@ -1,4 +1,5 @@
 #include "codec.hpp"
+#include "codec_par.hpp"
 
 #include <dlfcn.h>
 #include <zlib.h>
@@ -70,12 +71,14 @@ struct Libs {
     int (*BZ2_bzDecompress)(bz_stream*) = nullptr;
     int (*BZ2_bzDecompressEnd)(bz_stream*) = nullptr;
     int (*BZ2_bzBuffToBuffCompress)(char*, unsigned*, char*, unsigned, int, int, int) = nullptr;
+    int (*BZ2_bzBuffToBuffDecompress)(char*, unsigned*, char*, unsigned, int, int) = nullptr;
     // lzma
     int (*lzma_stream_decoder)(lzma_stream*, uint64_t, uint32_t) = nullptr;
     int (*lzma_code)(lzma_stream*, int) = nullptr;
     void (*lzma_end)(lzma_stream*) = nullptr;
     int (*lzma_easy_buffer_encode)(uint32_t, int, const void*, const uint8_t*, size_t, uint8_t*, size_t*, size_t) = nullptr;
     size_t (*lzma_stream_buffer_bound)(size_t) = nullptr;
+    int (*lzma_stream_buffer_decode)(uint64_t*, uint32_t, const void*, const uint8_t*, size_t*, size_t, uint8_t*, size_t*, size_t) = nullptr;
     // zstd
     void* (*ZSTD_createDStream)() = nullptr;
     size_t (*ZSTD_freeDStream)(void*) = nullptr;
@@ -83,6 +86,9 @@ struct Libs {
     size_t (*ZSTD_compress)(void*, size_t, const void*, size_t, int) = nullptr;
     size_t (*ZSTD_compressBound)(size_t) = nullptr;
     unsigned (*ZSTD_isError)(size_t) = nullptr;
+    size_t (*ZSTD_findFrameCompressedSize)(const void*, size_t) = nullptr;
+    unsigned long long (*ZSTD_getFrameContentSize)(const void*, size_t) = nullptr;
+    size_t (*ZSTD_decompress)(void*, size_t, const void*, size_t) = nullptr;
 };
 
 template <class F>
@@ -103,6 +109,7 @@ const Libs& libs(Format need) {
             sym(h, "BZ2_bzDecompress", L.BZ2_bzDecompress);
             sym(h, "BZ2_bzDecompressEnd", L.BZ2_bzDecompressEnd);
             sym(h, "BZ2_bzBuffToBuffCompress", L.BZ2_bzBuffToBuffCompress);
+            sym(h, "BZ2_bzBuffToBuffDecompress", L.BZ2_bzBuffToBuffDecompress);
         });
     if (need == Format::Lzma)
         std::call_once(xz, [] {
@@ -113,6 +120,7 @@ const Libs& libs(Format need) {
             sym(h, "lzma_end", L.lzma_end);
             sym(h, "lzma_easy_buffer_encode", L.lzma_easy_buffer_encode);
             sym(h, "lzma_stream_buffer_bound", L.lzma_stream_buffer_bound);
+            sym(h, "lzma_stream_buffer_decode", L.lzma_stream_buffer_decode);
         });
     if (need == Format::Zstd)
         std::call_once(zs, [] {
@@ -124,6 +132,9 @@ const Libs& libs(Format need) {
             sym(h, "ZSTD_compress", L.ZSTD_compress);
             sym(h, "ZSTD_compressBound", L.ZSTD_compressBound);
             sym(h, "ZSTD_isError", L.ZSTD_isError);
+            sym(h, "ZSTD_findFrameCompressedSize", L.ZSTD_findFrameCompressedSize);
+            sym(h, "ZSTD_getFrameContentSize", L.ZSTD_getFrameContentSize);
+            sym(h, "ZSTD_decompress", L.ZSTD_decompress);
         });
     return L;
 }
@@ -301,6 +312,12 @@ struct Reader::Impl {
         return true;
     }
 
+    // zstd frames / xz blocks / bzip2 blocks decoded side by side (codec_par.cpp); served unit by unit
+    std::unique_ptr<ParallelSource> par;
+    ParCodecs par_codecs;
+    std::vector<std::vector<uint8_t>> par_out;
+    size_t par_unit = 0, par_pos = 0;
+
     FILE* f = nullptr;
     std::vector<uint8_t> in;
     size_t in_pos = 0, in_len = 0;
@@ -334,6 +351,15 @@ Reader::Reader(const std::string& path) : p_(new Impl), fmt_(which_format(path))
             p_->bgzf = true;
             p_->pool.reset(new BgzfPool(inflate_threads()));
         }
+    }
+    if ((fmt_ == Format::Zstd || fmt_ == Format::Lzma || fmt_ == Format::Bzip) && inflate_threads() > 1) {
+        const Libs& L = libs(fmt_);
+        ParCodecs& c = p_->par_codecs;
+        c.ZSTD_findFrameCompressedSize = L.ZSTD_findFrameCompressedSize; c.ZSTD_getFrameContentSize = L.ZSTD_getFrameContentSize;
+        c.ZSTD_decompress = L.ZSTD_decompress; c.ZSTD_isError = L.ZSTD_isError;
+        c.lzma_stream_buffer_decode = L.lzma_stream_buffer_decode;
+        c.BZ2_bzBuffToBuffDecompress = L.BZ2_bzBuffToBuffDecompress;
+        p_->par = open_parallel(fmt_, path, c, inflate_threads());  // nullptr: the file does not split, stream it
     }
     if (fmt_ == Format::Zstd) {
         p_->zd = libs(fmt_).ZSTD_createDStream();
@@ -370,6 +396,31 @@ size_t Reader::read(uint8_t* dst, size_t n) {
         std::memcpy(dst + got, I.group_out.data() + I.group_pos, take);
         I.group_pos += take;
         got += take;
+    }
+    while (I.par && got < n) {
+        if (I.par_unit == I.par_out.size()) {
+            I.par_out.clear();
+            I.par_unit = I.par_pos = 0;
+            if (!I.par->next_group(I.par_out)) {  // the rest of the file (if any) is the sequential decoder's
+                const long at = (long)I.par->resume_offset();
+                I.par.reset();
+                fseek(I.f, 0, SEEK_END);
+                if (at >= ftell(I.f)) {  // nothing left: the streaming decoders never see a byte
+                    I.file_eof = true;
+                    I.stream_end = true;
+                    if (I.xz_open) { libs(Format::Lzma).lzma_end(&I.xz); I.xz_open = false; }
+                }
+                fseek(I.f, at, SEEK_SET);
+                break;
+            }
+            continue;
+        }
+        const std::vector<uint8_t>& u = I.par_out[I.par_unit];
+        const size_t take = std::min(n - got, u.size() - I.par_pos);
+        if (take) std::memcpy(dst + got, u.data() + I.par_pos, take);
+        I.par_pos += take;
+        got += take;
+        if (I.par_pos == u.size()) { ++I.par_unit; I.par_pos = 0; }
     }
     while (got < n) {
         if (!I.refill()) {

@@ -105,7 +105,11 @@ __device__ __forceinline__ uint32_t same_bin_lanes(uint32_t bin, uint32_t nbits,
 // writes the assignments and counts its bins in shared memory -> cta_cnt[bin][cta].
 // FUSED (cooperative launch, every CTA resident): kernel 3 follows in the same launch -- grid barrier, the per-bin
 // scans over CTAs spread over the grid, grid barrier, cursors from the counts still sitting in shared memory, scatter.
-template <int MODE, bool FUSED>
+// LEAN (packed modes only): the shared-memory diet for big tables that have to fit beside the record scan (overlapped
+// mode, one CTA per SM next to four of the scan's): per-warp bin counters are 16 bits wide (a warp's slice holds fewer
+// than 65536 records), cursors are kept as {32-bit CTA base per bin} + {16-bit offset per warp and bin}, and the region
+// prefix and the barcode table are read from global memory instead of a shared copy.
+template <int MODE, bool FUSED, bool LEAN>
 __global__ void __launch_bounds__(MATCH_THREADS) k_match(const MatchArgs A) {
     const RecSource& src = A.src;
     const BatchHeader* __restrict__ hdr = A.hdr;
@@ -120,23 +124,32 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(const MatchArgs A) {
     uint64_t* __restrict__ key_out = A.key_out;
     uint32_t* cta_cnt = A.cta_cnt;
     extern __shared__ __align__(16) uint8_t s_mem[];
-    // layout: [warps][nbins] histogram | region_base copy | table
+    // layout: [warps][nbins] histogram | region_base copy | table          (LEAN: [warps][nb2] u16 | [nbins] u32 CTA base)
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_mem);
     constexpr int WARPS = MATCH_THREADS / 32;
+    const uint32_t nb2 = (nbins + 1u) & ~1u;  // LEAN: 16-bit counters per warp row (even, so that rows stay word aligned)
+    uint16_t* const s_h16 = reinterpret_cast<uint16_t*>(s_mem);
+    uint32_t* const s_cta_base = s_hist + (size_t)WARPS * (nb2 / 2);  // LEAN only
     uint32_t* s_base = s_hist + (size_t)WARPS * nbins;
     const uint32_t mode = hdr->mode, nreg = mode ? hdr->n_regions : 0u;
     uint8_t* s_tab_raw = reinterpret_cast<uint8_t*>(s_base + MAX_REGIONS + 2);  // even word count: uint2 rows stay 8-byte aligned
     uint2* s_tab = reinterpret_cast<uint2*>(s_tab_raw);
     uint8_t* s_rows = s_tab_raw;
     uint32_t* s_lens = reinterpret_cast<uint32_t*>(s_tab_raw + (((size_t)n * stride + 3) & ~(size_t)3));
-    if (MODE == 2) {
-        for (uint32_t i = threadIdx.x; i < n * stride; i += blockDim.x) s_rows[i] = g_rows[i];
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_lens[i] = min(g_lens[i], k);  // zip stops at seq[..bc_len]
+    if (LEAN) {
+        for (uint32_t i = threadIdx.x; i < WARPS * (nb2 / 2); i += blockDim.x) s_hist[i] = 0;
     } else {
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_tab[i] = g_tab[i];
+        if (MODE == 2) {
+            for (uint32_t i = threadIdx.x; i < n * stride; i += blockDim.x) s_rows[i] = g_rows[i];
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_lens[i] = min(g_lens[i], k);  // zip stops at seq[..bc_len]
+        } else {
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_tab[i] = g_tab[i];
+        }
+        for (uint32_t i = threadIdx.x; i <= nreg; i += blockDim.x) s_base[i] = src.region_base[i];
+        for (uint32_t i = threadIdx.x; i < WARPS * nbins; i += blockDim.x) s_hist[i] = 0;
     }
-    for (uint32_t i = threadIdx.x; i <= nreg; i += blockDim.x) s_base[i] = src.region_base[i];
-    for (uint32_t i = threadIdx.x; i < WARPS * nbins; i += blockDim.x) s_hist[i] = 0;
+    const uint32_t* const rbase = LEAN ? src.region_base : s_base;  // exclusive record prefix over the regions
+    const uint2* const tab = LEAN ? g_tab : s_tab;
     __syncthreads();
     const uint32_t nrec = hdr->n_records;
     const bool fasta = hdr->fmt == SBR_FMT_FASTA;
@@ -144,7 +157,8 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(const MatchArgs A) {
     const bool want_keys = mode && ((hdr->status & SBR_ST_NONCANONICAL) || A.force_keys);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t V = gridDim.x * WARPS, v = blockIdx.x * WARPS + warp;
-    uint32_t* mine = s_hist + (size_t)warp * nbins;
+    uint32_t* mine = s_hist + (size_t)warp * (LEAN ? nb2 / 2 : nbins);  // LEAN: two 16-bit counters per word
+    uint16_t* const mine16 = s_h16 + (size_t)warp * nb2;
     uint32_t lo, hi;
     slice_range(nrec, V, v, lo, hi);
     // U records per lane and step: all loads of a step are issued before the first use
@@ -165,13 +179,13 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(const MatchArgs A) {
             if (g < hi) {
                 if (mode) {
                     if (g < reg_lo || g >= reg_hi) {  // regions hold thousands of records: rarely taken
-                        uint32_t a = 0, b = nreg;     // largest c with s_base[c] <= g
+                        uint32_t a = 0, b = nreg;     // largest c with rbase[c] <= g
                         while (b - a > 1) {
                             uint32_t mid = (a + b) >> 1;
-                            if (s_base[mid] <= g) a = mid; else b = mid;
+                            if (rbase[mid] <= g) a = mid; else b = mid;
                         }
-                        reg_lo = s_base[a];
-                        reg_hi = s_base[a + 1];
+                        reg_lo = rbase[a];
+                        reg_hi = rbase[a + 1];
                         reg_at = (size_t)a * src.cap_r;
                     }
                     const size_t at = reg_at + (g - reg_lo);
@@ -208,7 +222,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(const MatchArgs A) {
                 const uint32_t codes = (uint32_t)kk[u] & code_mask;
                 const uint32_t inval = (uint32_t)(kk[u] >> 32) & 0xFFFFu;
                 if (MODE == 1) {
-                    if (usable) hit = first_match(s_tab, n, m, codes, spread16(inval));
+                    if (usable) hit = first_match(tab, n, m, codes, spread16(inval));
                 } else {
                     if (usable && inval == 0) hit = __ldg(lut + codes);
                     // Reads with a non-ACGT base in the window: such a base differs from every barcode base
@@ -244,7 +258,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(const MatchArgs A) {
                             const uint32_t b = b0 + lane;
                             bool ok = false;
                             if (b < n) {
-                                const uint2 row = s_tab[b];
+                                const uint2 row = tab[b];
                                 const uint32_t x = cs ^ row.x;
                                 ok = (uint32_t)__popc(((x | (x >> 1)) | is) & row.y) <= m;
                             }
@@ -261,7 +275,8 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(const MatchArgs A) {
                     rec_off[g] = ro[u];
                     if (want_keys) key_out[g] = kk[u];
                 }
-                atomicAdd(&mine[hit], 1u);
+                if (LEAN) atomicAdd(&mine[hit >> 1], 1u << ((hit & 1u) * 16u));
+                else atomicAdd(&mine[hit], 1u);
             }
         }
     }
@@ -270,7 +285,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(const MatchArgs A) {
     for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) {
         uint32_t run = 0;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) run += s_hist[(size_t)w * nbins + b];
+        for (int w = 0; w < WARPS; ++w) run += LEAN ? (uint32_t)s_h16[(size_t)w * nb2 + b] : s_hist[(size_t)w * nbins + b];
         cta_cnt[(size_t)b * gridDim.x + blockIdx.x] = run;
     }
     if (!FUSED) return;
@@ -336,11 +351,22 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(const MatchArgs A) {
             if (b < nbins) {
                 if (blockIdx.x == 0) A.bin_start[b] = pre;
                 uint32_t run = pre + __ldcg(cta_cnt + (size_t)b * G + blockIdx.x);
+                if (LEAN) {  // the CTA's base for the bin + every warp's offset inside the CTA's run (fits 16 bits)
+                    s_cta_base[b] = run;
+                    uint32_t rel = 0;
 #pragma unroll
-                for (int w = 0; w < WARPS; ++w) {
-                    const uint32_t t = s_hist[(size_t)w * nbins + b];
-                    s_hist[(size_t)w * nbins + b] = run;
-                    run += t;
+                    for (int w = 0; w < WARPS; ++w) {
+                        const uint32_t t = s_h16[(size_t)w * nb2 + b];
+                        s_h16[(size_t)w * nb2 + b] = (uint16_t)rel;
+                        rel += t;
+                    }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < WARPS; ++w) {
+                        const uint32_t t = s_hist[(size_t)w * nbins + b];
+                        s_hist[(size_t)w * nbins + b] = run;
+                        run += t;
+                    }
                 }
             }
             carry += tot;
@@ -366,9 +392,13 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(const MatchArgs A) {
             const uint32_t bin = bins[u];
             const uint32_t peers = same_bin_lanes(bin, A.nbits, live);
             const uint32_t rank = __popc(peers & lt);
-            const uint32_t at = live ? mine[bin] : 0u;  // every lane of a group reads the group's cursor ...
+            uint32_t at = 0u;  // every lane of a group reads the group's cursor ...
+            if (live) at = LEAN ? s_cta_base[bin] + (uint32_t)mine16[bin] : mine[bin];
             __syncwarp();
-            if (live && rank == 0) mine[bin] = at + __popc(peers);  // ... then its first lane advances it
+            if (live && rank == 0) {  // ... then its first lane advances it
+                if (LEAN) mine16[bin] = (uint16_t)(mine16[bin] + __popc(peers));
+                else mine[bin] = at + __popc(peers);
+            }
             if (live) A.order[at + rank] = i;
             __syncwarp();
         }
@@ -402,22 +432,32 @@ struct MatchLaunch {
     // fused with kernel 3 (cooperative launch) when `fused`
     int fused; uint32_t nbits; uint32_t* bin_count; uint32_t* bin_start; uint32_t* order; BatchHeader* zero_next;
     uint32_t force_keys;  // write key_out whatever the header says (the host patched the stream's last record)
+    uint32_t lean;        // the shared-memory diet (k_match<.., LEAN>): see match_smem()
 };
 
-size_t match_smem(uint32_t n, uint32_t stride, uint32_t nbins, bool generic) {
+size_t match_smem(uint32_t n, uint32_t stride, uint32_t nbins, bool generic, bool lean) {
+    if (lean) return (size_t)(MATCH_THREADS / 32) * ((nbins + 1u) & ~1u) * 2u + (size_t)nbins * 4u + 16;
     size_t tab = generic ? ((((size_t)n * stride + 3) & ~(size_t)3) + n * 4u) : (size_t)n * sizeof(uint2);
     return (size_t)(MATCH_THREADS / 32) * nbins * 4u + (MAX_REGIONS + 2) * 4u + tab + 16;
 }
 
 using MatchKernel = void (*)(const MatchArgs);
-static MatchKernel match_kernel(int mode, bool fused) {
+static MatchKernel match_kernel(int mode, bool fused, bool lean = false) {
+    if (lean && mode < 2) {  // (the byte-exact kernel keeps its rows in shared memory: no lean variant)
+        switch (mode * 2 + (fused ? 1 : 0)) {
+            case 0: return k_match<0, false, true>;
+            case 1: return k_match<0, true, true>;
+            case 2: return k_match<1, false, true>;
+            default: return k_match<1, true, true>;
+        }
+    }
     switch (mode * 2 + (fused ? 1 : 0)) {
-        case 0: return k_match<0, false>;
-        case 1: return k_match<0, true>;
-        case 2: return k_match<1, false>;
-        case 3: return k_match<1, true>;
-        case 4: return k_match<2, false>;
-        default: return k_match<2, true>;
+        case 0: return k_match<0, false, false>;
+        case 1: return k_match<0, true, false>;
+        case 2: return k_match<1, false, false>;
+        case 3: return k_match<1, true, false>;
+        case 4: return k_match<2, false, false>;
+        default: return k_match<2, true, false>;
     }
 }
 
@@ -425,24 +465,24 @@ static MatchKernel match_kernel(int mode, bool fused) {
 // shared-memory split: ask for the same one, or the two could not be resident together
 cudaError_t match_prepare(bool max_shared) {
     cudaError_t e;
-    for (int mode = 0; mode < 3; ++mode)
-        for (int f = 0; f < 2; ++f) {
-            if ((e = cudaFuncSetAttribute(match_kernel(mode, f != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) !=
-                cudaSuccess)
-                return e;
-            if ((e = cudaFuncSetAttribute(match_kernel(mode, f != 0), cudaFuncAttributePreferredSharedMemoryCarveout,
-                                          max_shared ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault)) != cudaSuccess)
-                return e;
-        }
+    for (int lean = 0; lean < 2; ++lean)
+        for (int mode = 0; mode < (lean ? 2 : 3); ++mode)
+            for (int f = 0; f < 2; ++f) {
+                const MatchKernel kf = match_kernel(mode, f != 0, lean != 0);
+                if ((e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                              max_shared ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault)) != cudaSuccess)
+                    return e;
+            }
     return cudaFuncSetAttribute(k_build_lut, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
 }
 
 // the largest grid of the fused kernel that is resident all at once (a cooperative launch needs that); 0 = unsupported
-int match_fused_max_grid(int device, int mode, size_t smem) {
+int match_fused_max_grid(int device, int mode, size_t smem, bool lean) {
     int coop = 0, sms = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess || !coop) return 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel(mode, true), MATCH_THREADS, smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel(mode, true, lean), MATCH_THREADS, smem) != cudaSuccess) return 0;
     return per_sm * sms;
 }
 
@@ -461,12 +501,13 @@ cudaError_t match_launch(const MatchLaunch& L, cudaStream_t stream) {
     A.nbits = L.nbits; A.bin_count = L.bin_count; A.bin_start = L.bin_start; A.order = L.order;
     A.zero_next = L.fused ? L.zero_next : nullptr;
     A.force_keys = L.force_keys;
-    const size_t smem = match_smem(L.n, L.stride, L.nbins, generic);
+    const bool lean = L.lean && !generic;
+    const size_t smem = match_smem(L.n, L.stride, L.nbins, generic, lean);
     if (L.fused) {
         void* args[] = {&A};
-        return cudaLaunchCooperativeKernel((const void*)match_kernel(mode, true), dim3(L.grid), dim3(MATCH_THREADS), args, smem, stream);
+        return cudaLaunchCooperativeKernel((const void*)match_kernel(mode, true, lean), dim3(L.grid), dim3(MATCH_THREADS), args, smem, stream);
     }
-    match_kernel(mode, false)<<<L.grid, MATCH_THREADS, smem, stream>>>(A);
+    match_kernel(mode, false, lean)<<<L.grid, MATCH_THREADS, smem, stream>>>(A);
     return cudaGetLastError();
 }
 

@@ -62,10 +62,18 @@ __host__ __device__ constexpr int stage_stride(int fmt) { return (fmt == SBR_FMT
 #ifndef SBR_WL_CAP
 #define SBR_WL_CAP (SBR_SCAN_SINGLE ? 284 : 188)
 #endif
-constexpr int WL_CAP = SBR_WL_CAP;  // newline positions per warp slice held in shared memory (>= 16.3-byte lines on average)
+constexpr int WL_CAP = SBR_WL_CAP;
+// FASTA keeps a second per-slice array (ridx): its lists are shorter (>= 24-byte lines on average, denser slices are the
+// exact scan's job) so that four of its CTAs leave as much shared memory to the match kernel running beside them as
+// four FASTQ CTAs do
+#ifndef SBR_WL_CAP_FASTA
+#define SBR_WL_CAP_FASTA (SBR_SCAN_SINGLE ? 192 : 128)
+#endif
+constexpr int WL_CAP_FASTA = SBR_WL_CAP_FASTA < WL_CAP ? SBR_WL_CAP_FASTA : WL_CAP;
+__host__ __device__ constexpr int wl_cap(int fmt) { return fmt == SBR_FMT_FASTA ? WL_CAP_FASTA : WL_CAP; }
 constexpr int CNT_BITS = FAST_UNITS == 2 ? 16 : 10;   // per-unit newline counts of a slice share one word (valid while the slice fits WL_CAP)
 constexpr uint32_t CNT_MASK = (1u << CNT_BITS) - 1u;
-constexpr int FASTA_CHUNKS = (WL_CAP + 31) / 32;
+constexpr int FASTA_CHUNKS = (WL_CAP_FASTA + 31) / 32;
 constexpr uint32_t FASTA_START = 1u << 30;  // list entry flag: a FASTA record starts behind this newline
 constexpr uint32_t POS_MASK = FASTA_START - 1u;  // the position part of a list entry (batches are at most 1 GiB)
 
@@ -73,11 +81,11 @@ template <int FMT>
 struct FastSmem {
     uint64_t full_bar[FAST_STAGES];
     // per warp: [GHOSTS - 1 - g] = g-th most recent newline before the slice, [GHOSTS + i] = i-th newline of the slice
-    uint32_t wl[FAST_WARPS][GHOSTS + WL_CAP];
+    uint32_t wl[FAST_WARPS][GHOSTS + wl_cap(FMT)];
     uint32_t wtot[2][FAST_WARPS];           // by tile parity: newlines | record starts << 16 of each warp slice
     uint32_t wtail[2][FAST_WARPS][GHOSTS];  // by tile parity: the slice's last four newline positions, [0] most recent
     uint32_t whead[2][FAST_WARPS][2];       // by tile parity: the slice's first two newline positions (FASTA looks ahead)
-    uint16_t ridx[FMT == SBR_FMT_FASTA ? FAST_WARPS : 1][FMT == SBR_FMT_FASTA ? WL_CAP + 4 : 2];  // FASTA: list index of the u-th record start
+    uint16_t ridx[FMT == SBR_FMT_FASTA ? FAST_WARPS : 1][FMT == SBR_FMT_FASTA ? WL_CAP_FASTA + 4 : 2];  // FASTA: list index of the u-th record start
     uint32_t gh[2][GHOSTS];                 // by tile parity: the four most recent newlines before the tile
     uint32_t cnt[2];                        // newlines of the region before the tile
     uint32_t rcnt[2];                       // FASTA: record starts of the region before the tile
@@ -438,7 +446,7 @@ __global__ void __maxnreg__(SBR_SCAN_NREG) k_scan_fast(FastArgs A) {
         // read before the barrier: thread 0 may flip it right after that barrier, and every thread has to take
         // the same decision about the extra barrier below
         const bool was_synced = S.synced != 0;
-        const bool fits = n_w <= (uint32_t)WL_CAP;  // warp-uniform
+        const bool fits = n_w <= (uint32_t)wl_cap(FMT);  // warp-uniform
 
         // ---- compact the slice's newline positions (ascending) into the warp's list ---------------------
         uint32_t start_bal[FASTA_CHUNKS] = {};  // FASTA: per 32 list entries, which ones are record starts
@@ -558,7 +566,7 @@ __global__ void __maxnreg__(SBR_SCAN_NREG) k_scan_fast(FastArgs A) {
                     const ByteSrc B{sm, A.text, lo, lo + valid};
                     uint32_t nf = S.nfirst;
                     for (int v = 0; v < FAST_WARPS && nf < 8; ++v) {
-                        const uint32_t nv = min(S.wtot[par][v] & 0xFFFFu, (uint32_t)WL_CAP);
+                        const uint32_t nv = min(S.wtot[par][v] & 0xFFFFu, (uint32_t)wl_cap(FMT));
                         for (uint32_t i = 0; i < nv && nf < 8; ++i) S.first[nf++] = S.wl[v][GHOSTS + i];
                     }
                     S.nfirst = nf;

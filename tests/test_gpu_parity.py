@@ -162,6 +162,35 @@ def test_overlapped_pipeline_equals_oracle(gpu, name, n, nb, extra):
             assert np.array_equal(b.assign, exp["assign"]) and np.array_equal(b.order, exp["order"])
 
 
+@pytest.mark.parametrize("name,flags", [("cfg3", 0), ("cfg3", 1), ("cfg4", 0), ("cfg5", 0), ("cfg5", 0x10)])
+def test_lean_match_kernel_equals_oracle(gpu, name, flags, monkeypatch):
+    """the match kernel's shared-memory diet (16-bit per-warp counters, CTA base + 16-bit offsets as cursors, table and
+    region prefix read from global memory) -- what big tables (cfg5: 1537 bins) use beside the scan -- forced onto every
+    table size, LUT and table-walk matching"""
+    torch, synth, dmx, ffi = gpu["torch"], gpu["synth"], gpu["demux"], gpu["ffi"]
+    monkeypatch.setenv("SBR_FORCE_LEAN", "1")
+    w = synth.WORKLOADS[name]
+    tab = synth.table(w)
+    bcs = [bytes(r) for r in tab]
+    rec = w.rec_bytes
+    n, nb = 40_000, 4
+    dev = torch.empty(n * nb * rec + 64, dtype=torch.uint8, device="cuda")
+    synth.reads_device(w, tab, 31_000_000, n * nb, dev.data_ptr())
+    host = dev[: n * nb * rec].cpu().numpy()
+    st = torch.cuda.Stream()
+    with dmx.Demux(bcs, w.mismatch, fmt=w.fmt, batch_bytes=n * rec + 4096, n_slots=2, max_records=n + 16,
+                   flags=ffi.CFG_OVERLAP | flags) as dm:
+        for i in range(nb):
+            dm.demux_device(i % 2, dev.data_ptr() + i * n * rec, n * rec, final=True, stream=st.cuda_stream)
+            if i >= 1:
+                b = dm.wait((i - 1) % 2)
+                exp = orc.demux(host[(i - 1) * n * rec:i * n * rec], bcs, w.mismatch)
+                assert b.n_records == n and b.status == 0
+                assert np.array_equal(b.assign, exp["assign"]) and np.array_equal(b.bin_count, exp["bin_count"])
+                assert np.array_equal(b.bin_start, exp["bin_start"]) and np.array_equal(b.order, exp["order"])
+        dm.wait((nb - 1) % 2)
+
+
 def test_scan_stats_count_handed_over_batches(gpu):
     """the device-side counters bench.py reads: a malformed batch is handed to the exact scan and counted"""
     torch, dmx, ffi = gpu["torch"], gpu["demux"], gpu["ffi"]

@@ -257,3 +257,95 @@ def test_bgzf_corruption_is_an_error(tmp_path):
     p.write_bytes(bytes(bad))
     r = subprocess.run([SELFTEST, "cat", str(p)], capture_output=True)
     assert r.returncode != 0 and b"corrupt" in r.stderr
+
+
+# ---- round 2: block-parallel decompression of splittable inputs (codec_par.cpp) ----------------------------------
+def _text(n_rec=60000, seed=5):
+    import random
+    rng = random.Random(seed)
+    out = bytearray()
+    for i in range(n_rec):
+        L = rng.randint(40, 120)
+        out += b"@r%d\n" % i + bytes(rng.choices(b"ACGTN", k=L)) + b"\n+\n" + bytes(rng.choices(range(33, 74), k=L)) + b"\n"
+    return bytes(out)
+
+
+def _cat_par(path, threads, chunk=None):
+    env = dict(os.environ, SABREUR_INFLATE_THREADS=str(threads))
+    args = [SELFTEST, "cat", str(path)] + ([str(chunk)] if chunk else [])
+    return subprocess.run(args, capture_output=True, env=env)
+
+
+@pytest.mark.parametrize("threads", [1, 2, 5])
+def test_bzip2_blocks_decode_in_parallel(tmp_path, threads):
+    """multi-block streams (every block found by its 48-bit magic at any bit offset and decoded as a stream of its own),
+    concatenated streams with different levels, an empty stream in between, runs that expand past the block size"""
+    text = _text()
+    runs = b"A" * 3_000_000 + text[:100_000] + b"\0" * 1_500_000  # RLE1: a 100 k block holds far more than 100 kB of these
+    cases = {
+        "level1.bz2": bz2.compress(text, 1),            # ~70 blocks of 100 kB
+        "level9.bz2": bz2.compress(text, 9),
+        "concat.bz2": bz2.compress(text[:1_000_003], 2) + bz2.compress(b"", 9) + bz2.compress(text[1_000_003:], 4),
+        "runs.bz2": bz2.compress(runs, 1),
+    }
+    want = {"level1.bz2": text, "level9.bz2": text, "concat.bz2": text, "runs.bz2": runs}
+    for name, blob in cases.items():
+        p = tmp_path / name
+        p.write_bytes(blob)
+        r = _cat_par(p, threads, 50_001)
+        assert r.returncode == 0, r.stderr
+        assert hashlib.sha256(r.stdout).hexdigest() == hashlib.sha256(want[name]).hexdigest(), name
+
+
+def test_bzip2_damaged_block_is_an_error_not_garbage(tmp_path):
+    blob = bytearray(bz2.compress(_text(20000), 1))
+    blob[len(blob) // 2] ^= 0x55
+    p = tmp_path / "bad.bz2"
+    p.write_bytes(bytes(blob))
+    for threads in (1, 4):
+        r = _cat_par(p, threads)
+        assert r.returncode != 0 and b"bzip2" in r.stderr
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_xz_blocks_and_streams_decode_in_parallel(tmp_path, threads):
+    """xz -T style multi-block streams (block sizes come from the stream's index, read from the end of the file
+    backwards), concatenated streams, stream padding, different integrity checks"""
+    import shutil
+    text = _text()
+    cases = {}
+    cases["streams.xz"] = b"".join(lzma.compress(text[i:i + 700_001], preset=0) for i in range(0, len(text), 700_001))
+    cases["padded.xz"] = lzma.compress(text[:2_000_000], preset=0) + b"\0" * 8 + lzma.compress(text[2_000_000:], preset=1,
+                                                                                               check=lzma.CHECK_SHA256) + b"\0" * 4
+    cases["crc32.xz"] = lzma.compress(text[:999], check=lzma.CHECK_CRC32) + lzma.compress(text[999:], check=lzma.CHECK_NONE)
+    if shutil.which("xz"):
+        plain = tmp_path / "plain.txt"
+        plain.write_bytes(text)
+        cases["blocks.xz"] = subprocess.run(["xz", "-0", "-T3", "--block-size=524288", "-c", str(plain)], capture_output=True, check=True).stdout
+    for name, blob in cases.items():
+        p = tmp_path / name
+        p.write_bytes(blob)
+        if name != "padded.xz":  # (Python's one-shot decoder stops at stream padding; the format allows it)
+            assert lzma.decompress(blob) == text  # the case itself is a valid file
+        r = _cat_par(p, threads, 65_537)
+        assert r.returncode == 0, r.stderr
+        assert hashlib.sha256(r.stdout).hexdigest() == hashlib.sha256(text).hexdigest(), name
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_zstd_frames_decode_in_parallel(tmp_path, threads):
+    text = _text()
+    for member in (65_536, 4 << 20):
+        p = tmp_path / f"m{member}.zst"
+        with open(p, "wb") as fh:
+            subprocess.run([SELFTEST, "pack", "zst", "2", str(member)], input=text, stdout=fh, check=True)
+        r = _cat_par(p, threads, 100_003)
+        assert r.returncode == 0, r.stderr
+        assert hashlib.sha256(r.stdout).hexdigest() == hashlib.sha256(text).hexdigest()
+    # a file cut inside a frame is an error under both readers (frames written by ZSTD_compress carry no checksum, so
+    # flipped payload bits are not something either reader could notice)
+    blob = open(tmp_path / "m65536.zst", "rb").read()
+    p = tmp_path / "cut.zst"
+    p.write_bytes(blob[: len(blob) * 2 // 3])
+    r = _cat_par(p, threads)
+    assert r.returncode != 0 and text.startswith(r.stdout) and len(r.stdout) > len(text) // 2

@@ -50,6 +50,7 @@ def parse_args():
                                                               "(default: on the slot's own stream, beside the next scan)")
     ap.add_argument("--no-fuse", action="store_true", help="match and partition as separate launches")
     ap.add_argument("--slots", type=int, default=3, help="device workspaces the HBM-resident loop rotates through")
+    ap.add_argument("--no-verify-merge", action="store_true", help="skip the multi-GPU merge check (sabreur_b200/shard.py)")
     return ap.parse_args()
 
 
@@ -344,6 +345,67 @@ def h2d_ceiling(env: Env, seconds: float = 0.4) -> dict:
             "h2d_ceiling_how": f"{env.world} rank(s) x {reps} pinned 256 MiB cudaMemcpyAsync on 2 streams each, all at once, max over ranks"}
 
 
+def verify_merge(env: Env, n_reads: int = 1_048_576, n_batches: int = 16) -> dict:
+    """The multi-GPU product path in small: a slice of cfg3 is cut into batches, batch s runs on rank s mod N through the
+    streaming API (pinned host text -> sbr_submit -> sbr_wait), the per-batch results are gathered on rank 0 and merged
+    back into the sequential reference's view by sabreur_b200/shard.py (counts summed, per-barcode index lists appended in
+    batch order).  Checked without the oracle: the merged lists must be ascending, cover every read exactly once, agree
+    with the all-reduced counts, and every read's bin must be the first barcode row within the mismatch budget of its
+    prefix (src/demux.rs:52-54), recomputed here with numpy."""
+    import numpy as np
+    from sabreur_b200 import _ffi, demux, shard, synth
+    w = synth.CFG3
+    tab = synth.table(w)
+    bcs = [bytes(r) for r in tab]
+    rec, k = w.rec_bytes, w.bc_len
+    per = n_reads // n_batches
+    first = 77_000_000
+    mine = list(shard.batches_of_rank(n_batches, env.world, env.rank))
+    results = []
+    with demux.Demux(bcs, w.mismatch, fmt=w.fmt, device=env.local_rank, batch_bytes=per * rec + 4096, n_slots=2,
+                     max_records=per + 16) as dm:
+        for j, s in enumerate(mine):  # two slots: batch j+1 is submitted before batch j is waited for
+            buf = dm.slot_buffer(j % 2)
+            buf[: per * rec] = synth.reads_host(w, tab, first + s * per, per)
+            dm.submit(j % 2, 0, per * rec, s, True)
+            if j >= 1:
+                b = dm.wait((j - 1) % 2)
+                results.append(shard.BatchResult(int(b.seq), b.n_records, b.bin_count, b.bin_start, b.order, b.status, b.first_bad_record))
+        if mine:
+            b = dm.wait((len(mine) - 1) % 2)
+            results.append(shard.BatchResult(int(b.seq), b.n_records, b.bin_count, b.bin_start, b.order, b.status, b.first_bad_record))
+        n_bins = dm.n_bins
+    local_counts = np.zeros(n_bins, dtype=np.uint64)
+    for r in results:
+        local_counts += r.bin_count.astype(np.uint64)
+    total_counts = shard.merge_counts(local_counts)
+    everything = shard.gather_results(results, dst=0)
+    if env.rank != 0:
+        return {}
+    merged = shard.merge_in_order(sorted(everything, key=lambda r: (r.seq % env.world, r.seq)), n_bins)  # arrival order: rank by rank
+    lists = merged.lists()
+    ok = merged.n_records == n_reads and merged.status == 0 and np.array_equal(merged.bin_count, total_counts)
+    assign = np.full(n_reads, 0xFFFF, dtype=np.uint16)
+    for b_, idx in enumerate(lists):
+        ok = ok and (idx.size < 2 or bool((np.diff(idx.astype(np.int64)) > 0).all()))  # input order inside every file
+        assign[idx.astype(np.int64)] = b_
+    ok = ok and not (assign == 0xFFFF).any()
+    text = synth.reads_host(w, tab, first, n_reads).reshape(n_reads, rec)
+    pre = text[:, 17:17 + k]
+    want = np.full(n_reads, len(bcs), dtype=np.uint16)
+    todo = np.ones(n_reads, dtype=bool)
+    for b_ in range(len(bcs)):
+        hit = todo & ((pre != tab[b_]).sum(1) <= w.mismatch)
+        want[hit] = b_
+        todo &= ~hit
+    ok = ok and np.array_equal(assign, want)
+    if not ok:
+        raise AssertionError("verify_merge: the merged multi-GPU partition is not the sequential one")
+    return {"reads": n_reads, "batches": n_batches, "ranks": env.world, "ok": True,
+            "how": "batch s on rank s mod N through sbr_submit/sbr_wait; shard.gather_results + merge_in_order + merge_counts; "
+                   "merged lists ascending, complete, equal to the all-reduced counts and to numpy's first-match over the prefixes"}
+
+
 def run_block(env: Env, name: str, units: int, primary: bool) -> dict:
     """one workload: generate the shard on the device, self-check every batch, time K steps HBM-resident, then end to end"""
     import numpy as np
@@ -409,7 +471,9 @@ def run_block(env: Env, name: str, units: int, primary: bool) -> dict:
     # ---- warm-up 1: every batch of the step once, each one waited for and checked --------------------------
     unknown = 0
     for i in range(len(batches)):
-        unknown += check(i, dm.wait(launch(i), copy=False))
+        slot = launch(i)
+        unknown += check(i, dm.wait(slot, copy=False))
+        holds[slot] = None  # waited for: nothing in flight there
     for _ in range(max(0, args.warmup - 1)):
         step()
     dm.join(stream)
@@ -603,6 +667,7 @@ def main():
     also = args.also if args.also is not None else ("cfg4,cfg5" if args.workload == "cfg3" else "none")
     others = [x for x in also.split(",") if x and x != "none" and x != args.workload]
 
+    merged = None if args.no_verify_merge else verify_merge(env)
     ceiling = None if args.no_e2e else h2d_ceiling(env)
     main_block = run_block(env, args.workload, primary_units, True)
     blocks = {}
@@ -623,6 +688,7 @@ def main():
             "config": main_block["config"], "roofline": main_block["roofline"], "self_check": main_block["self_check"],
             "cpu_baseline": main_block["cpu_baseline"], "e2e": main_block["e2e"], "clocks": main_block["clocks"],
             "gpu_launches": main_block["gpu_launches"] + sum(b["gpu_launches"] for b in blocks.values()),
+            "verify_merge": merged,
             "workloads": {k: {kk: vv for kk, vv in b.items() if kk != "cpu_baseline"} for k, b in blocks.items()},
         }
         sys.stdout.flush()

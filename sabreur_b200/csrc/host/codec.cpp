@@ -242,7 +242,7 @@ private:
 int inflate_threads() {
     if (const char* e = getenv("SABREUR_INFLATE_THREADS")) return std::max(1, atoi(e));
     const unsigned hw = std::thread::hardware_concurrency();
-    return (int)std::max(1u, std::min(8u, hw ? hw : 1u));
+    return (int)std::max(1u, std::min(16u, hw ? hw : 1u));
 }
 
 }  // namespace

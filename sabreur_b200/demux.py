@@ -173,25 +173,22 @@ class Demux:
         The unconsumed tail of batch i (an incomplete record) is prepended to batch i+1: room for it is
         reserved at the front of every slot, so freshly read bytes are never moved.  Batches are therefore
         chained (i+1 is submitted once i's `consumed` is known); the exactness of record boundaries comes
-        from the GPU scan alone, never from a host-side guess.
+        from the GPU scan alone, never from a host-side guess.  What does overlap: while the GPU works on batch i
+        the host already reads (decompresses) the fresh bytes of batch i+1 into the next slot, behind the reserved room.
         Yields Batch objects whose .text views the slot memory: use it before asking for the next batch.
         """
         cap = self.batch_bytes
         reserve = cap // 4 if reserve is None else reserve
         it = iter(chunks)
         pending = b""      # bytes read from `chunks` but not yet placed in a slot
-        tail = np.zeros(0, dtype=np.uint8)
         eof = False
-        seq = 0
-        base = 0
-        slot = 0
-        while True:
+
+        def fill(slot: int) -> tuple[int, bool]:
+            """fresh bytes into the slot behind the reserved room -> (bytes placed, the stream ends with them)"""
+            nonlocal pending, eof
             buf = self.slot_buffer(slot)
-            off = reserve - tail.size if tail.size <= reserve else 0
-            buf[off:off + tail.size] = tail
-            start = off + tail.size
             filled = 0
-            while start + filled < cap and not eof:
+            while reserve + filled < cap and (pending or not eof):
                 if not pending:
                     try:
                         pending = next(it)
@@ -200,8 +197,8 @@ class Demux:
                         break
                     if not pending:
                         continue
-                take = min(len(pending), cap - start - filled)
-                buf[start + filled: start + filled + take] = np.frombuffer(pending[:take], dtype=np.uint8)
+                take = min(len(pending), cap - reserve - filled)
+                buf[reserve + filled: reserve + filled + take] = np.frombuffer(pending[:take], dtype=np.uint8)
                 pending = pending[take:]
                 filled += take
             if not pending and not eof:  # learn about EOF before deciding whether this batch is final
@@ -209,13 +206,37 @@ class Demux:
                     pending = next(it)
                 except StopIteration:
                     eof = True
-            final = eof and not pending
+            return filled, eof and not pending
+
+        tail = np.zeros(0, dtype=np.uint8)
+        seq = 0
+        base = 0
+        slot = 0
+        filled, final = fill(slot)
+        while True:
+            buf = self.slot_buffer(slot)
+            if tail.size <= reserve:
+                off = reserve - tail.size
+                buf[off:reserve] = tail
+            else:  # a tail larger than the reserved room (a record of more than a quarter batch): slide the fresh bytes back
+                over = max(0, tail.size + filled - cap)
+                if over:  # ... and hand what no longer fits back to the reader
+                    pending = buf[reserve + filled - over: reserve + filled].tobytes() + pending
+                    filled -= over
+                    final = False
+                buf[tail.size: tail.size + filled] = buf[reserve: reserve + filled].copy()
+                buf[:tail.size] = tail
+                off = 0
             nbytes = tail.size + filled
             if nbytes == 0:
                 if seq == 0:
                     raise ParseError(_ffi.ST_INVALID_START, 0)  # empty input: needletail refuses it
                 return
             self.submit(slot, off, nbytes, seq, final)
+            nxt = (slot + 1) % self.n_slots
+            prefilled = None
+            if not final and nxt != slot:
+                prefilled = fill(nxt)  # the host reads ahead while the GPU scans
             b = self.wait(slot)
             b.text = buf[off: off + nbytes]
             b.record_base = base
@@ -227,9 +248,10 @@ class Demux:
             if b.consumed == 0 and not final:
                 raise SabreurGpuError("no progress: a single record is larger than a batch")
             seq += 1
-            slot = (slot + 1) % self.n_slots
             if final and not ((b.status & _ffi.ST_REC_OVERFLOW) and tail.size):
                 return
+            slot = nxt
+            filled, final = prefilled if prefilled is not None else fill(slot)
 
 
 def demux_bytes(data: bytes, barcodes: list[bytes], mismatch: int, fmt: int = FMT_AUTO, batch_bytes: int = 8 << 20,

@@ -45,10 +45,33 @@ def plain(path: str) -> bytes:
 
 
 def write_input(rng: random.Random, path: str, text: bytes) -> str:
-    how = rng.choice(("plain", "plain", "gz", "gz_members"))
+    how = rng.choice(("plain", "plain", "gz", "gz_members", "bz2_blocks", "bz2_streams", "xz_streams", "xz_blocks", "zst_frames"))
     if how == "plain":
         open(path, "wb").write(text)
         return path
+    # the splittable formats: many blocks / streams / frames, so that the block-parallel readers (codec_par.cpp) have work
+    if how == "bz2_blocks":
+        open(path + ".bz2", "wb").write(bz2.compress(text, 1))
+        return path + ".bz2"
+    if how in ("bz2_streams", "xz_streams"):
+        comp = (lambda b: bz2.compress(b, rng.randint(1, 9))) if how == "bz2_streams" else (lambda b: lzma.compress(b, preset=0))
+        ext = ".bz2" if how == "bz2_streams" else ".xz"
+        cuts = sorted(rng.randrange(len(text) + 1) for _ in range(rng.randint(1, 8)))
+        with open(path + ext, "wb") as f:
+            for a, b in zip([0] + cuts, cuts + [len(text)]):
+                f.write(comp(text[a:b]))
+        return path + ext
+    if how == "xz_blocks":
+        if shutil.which("xz") is None:
+            open(path, "wb").write(text)
+            return path
+        open(path, "wb").write(text)
+        subprocess.run(["xz", "-0", "-T2", "--block-size=262144", "-f", path], check=True)
+        return path + ".xz"
+    if how == "zst_frames":
+        with open(path + ".zst", "wb") as f:
+            subprocess.run([SELFTEST, "pack", "zst", "1", str(rng.choice((70_001, 1 << 20)))], input=text, stdout=f, check=True)
+        return path + ".zst"
     path += ".gz"
     with open(path, "wb") as f:
         if how == "gz":
@@ -121,7 +144,12 @@ def run_case(seed: int, workdir: str):
             files[stem] = os.path.join(out, name)
         for mate, t in enumerate(goods):
             if want_rc == 101 and paired and mate == 1:
-                break  # the forward pass panicked: the reverse pass never ran (or was cut short)
+                # the forward pass panicked: the reference never reaches the reverse loop (demux.rs:101-123), and the
+                # host takes back whatever its side-by-side reverse pass had written
+                for stem, path_ in files.items():
+                    if "_R2" in stem and os.path.getsize(path_) != 0:
+                        return f"{stem} is not empty although the forward pass panicked", params
+                break
             exp = orc.demux_outputs(t, bcs, m) if t else [b""] * (len(bcs) + 1)
             for i in range(len(bcs)):
                 stem = f"b{i}_R{mate + 1}{ext}"

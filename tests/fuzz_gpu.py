@@ -19,6 +19,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import oracle as orc  # noqa: E402
 from sabreur_b200 import _ffi, demux as dm  # noqa: E402
 
+# kernel variants every case runs through: the look-back scan, the region-parallel scan with the fused and the separate
+# partition, and (CFG_OVERLAP + SBR_FORCE_LEAN) the one-CTA-per-SM grid with the lean 16-bit-counter match kernel
+os.environ.setdefault("SBR_FORCE_LEAN", "1")
+VARIANTS = ((_ffi.CFG_EXACT_SCAN, 0), (0, 0), (0, _ffi.CFG_NO_FUSE), (0, _ffi.CFG_OVERLAP))
+
 BASES = b"ACGT"
 ODD = b"NnacgtRYKM-."
 
@@ -159,7 +164,7 @@ def check_violation(text, bcs, m, batch, chunk, user_flags, starts):
         return f"oracle names record {err.record} of {len(starts)}"
     cut = starts[err.record] if err.record < len(starts) else None
     exp = orc.demux(text[:cut], bcs, m) if (cut is None or cut > 0) and err.record > 0 else None
-    for scan_flag, extra in ((_ffi.CFG_EXACT_SCAN, 0), (0, 0), (0, _ffi.CFG_NO_FUSE)):
+    for scan_flag, extra in VARIANTS:
         got = dm.demux_bytes(text, bcs, m, batch_bytes=batch, chunk=chunk, flags=user_flags | scan_flag | extra)
         tag = f"flags={user_flags | scan_flag | extra:#x}"
         if got["bad"] is None:
@@ -175,7 +180,7 @@ def check_violation(text, bcs, m, batch, chunk, user_flags, starts):
 
 def check(text, bcs, m, batch, chunk, user_flags):
     exp = orc.demux(text, bcs, m)
-    for scan_flag, extra in ((_ffi.CFG_EXACT_SCAN, 0), (0, 0), (0, _ffi.CFG_NO_FUSE)):
+    for scan_flag, extra in VARIANTS:
         got = dm.demux_bytes(text, bcs, m, batch_bytes=batch, chunk=chunk, flags=user_flags | scan_flag | extra)
         tag = f"flags={user_flags | scan_flag | extra:#x}"
         if got["bad"] is not None or (got["status"] & _ffi.ST_ERROR_MASK):

@@ -416,6 +416,23 @@ def test_adversarial_phase_detection(gpu):
     _check_against_oracle(gpu, bytes(out), bcs, 1, batch_bytes=1 << 20, chunk=333_333)
 
 
+def test_records_larger_than_the_reserved_room_in_front_of_a_slot(gpu):
+    """Demux.stream reads the next batch's fresh bytes behind a reserved quarter of the slot while the GPU works; a tail
+    (incomplete record) larger than that room makes it slide the fresh bytes back and hand the overflow to the reader"""
+    rng = random.Random(21)
+    bcs = [bytes(rng.choices(b"ACGT", k=8)) for _ in range(20)]
+    out = bytearray()
+    for i in range(400):
+        L = rng.choice((40, 200, 9000, 13000))  # 26 KB records against 64 KB batches (16 KB reserved)
+        s_ = rng.choice(bcs) + bytes(rng.choices(b"ACGT", k=L))
+        out += b"@r%d\n" % i + s_ + b"\n+\n" + bytes(rng.choices(range(35, 74), k=len(s_))) + b"\n"
+    _check_against_oracle(gpu, bytes(out), bcs, 1, batch_bytes=1 << 16, chunk=7001)
+    fa = bytearray()
+    for i in range(300):
+        fa += b">r%d\n" % i + rng.choice(bcs) + bytes(rng.choices(b"ACGT", k=rng.choice((30, 20000, 27000)))) + b"\n"
+    _check_against_oracle(gpu, bytes(fa), bcs, 0, batch_bytes=1 << 16, chunk=100_000)
+
+
 def test_record_capacity_overflow_is_chunked_not_lost(gpu):
     rng = random.Random(9)
     text = _rand_fastq(rng, 5000, lo=8, hi=12)

@@ -546,6 +546,29 @@ def run_block(env: Env, name: str, units: int, primary: bool) -> dict:
         except Exception:
             pass
     dm.close()
+    if overlap:
+        # the scan kernel on its own: the same batches through a one-stream context (match + partition BEHIND the scan
+        # instead of beside the next one), a few batches only -- the figure that compares with round 1's and with ncu's
+        # serialised launch list; `frac` above is the kernel's time in the timed loop, where it shares the SMs
+        dm1 = demux.Demux(bcs, w.mismatch, fmt=w.fmt, device=env.local_rank, batch_bytes=bu * rec + 4096, n_slots=2,
+                          max_records=bu + 16, flags=flags & ~_ffi.CFG_OVERLAP)
+        nb1 = min(len(batches), 12)
+        for rnd in range(2):
+            if rnd == 1:
+                torch.cuda.synchronize()
+                dm1.timing()
+            for i in range(nb1):
+                ti, off, nb = batches[i]
+                dm1.demux_device(i % 2, texts[ti].data_ptr() + off, nb, final=True, stream=stream)
+        torch.cuda.synchronize()
+        k1, n1, _ = dm1.timing()
+        dm1.close()
+        if n1 and k1[0] > 0:
+            reads1 = sum(batches[i][2] // rec for i in range(nb1)) / nb1
+            alone = reads1 * scan_bytes_per_read / (k1[0] / n1 * 1e-3) / 1e9
+            roofline["alone"] = {"achieved": alone, "frac": alone / env.peak, "avg_launch_ms": k1[0] / n1, "batches": n1,
+                                 "match_partition_ms": (k1[1] + k1[2]) / n1,
+                                 "how": "the same kernel in a one-stream loop (nothing else on the SMs), untimed extra pass"}
 
     # ---- end to end: pinned host text -> sbr_submit -> sbr_wait (H2D + kernels + D2H every batch) -------
     e2e = None

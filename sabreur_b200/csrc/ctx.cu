@@ -482,7 +482,7 @@ static int launch_pipeline(sbr_ctx* c, Slot& s, const uint8_t* d_text, uint32_t 
         uint32_t nreg = scan_fast_regions(nbytes, fmt == SBR_FMT_FASTA ? c->fast_grid_a : c->fast_grid_q, &tpr, &extra);
         // segments get 25 % + 64 records of slack over an even split: regions hold unequal record counts
         s.cur_cap_r = (uint32_t)(((uint64_t)c->max_records * 5 / 4) / nreg) + 64;
-        // (k_scan_finish clears the look-back scan's tile descriptors when it hands the batch over)
+        // (the scan's epilogue clears the look-back scan's tile descriptors when it hands the batch over)
         CU(c, scan_fast_launch(fmt, d_text, nbytes, c->max_records, s.cur_cap_r, nreg, tpr, extra, c->cfg.bc_len,
                                c->packed ? 1u : 0u, (uint32_t)final_batch, s.d_hdr, s.d_info, s.d_region_base, s.d_seg_rec_off,
                                s.d_seg_key, s.d_rec_off, s.d_desc, scan_tiles(nbytes), c->d_stats, st));

@@ -17,7 +17,8 @@
 //     between barriers;
 //   * FASTQ: where in the 4-line cycle a region starts is not known locally ('@' and '+' are legal
 //     quality characters), so the CTA DETECTS it from its first eight newlines (the one phase under
-//     which the first whole record parses) and k_scan_finish VERIFIES every region's phase against the
+//     which the first whole record parses) and the batch's epilogue (scan_finish, run by the last CTA to
+//     finish its region) VERIFIES every region's phase against the
 //     exact prefix sum of the regions' newline counts.  A batch where any region is wrong, malformed,
 //     short, over capacity or undecidable is flagged (hdr->spec_fail) and re-scanned by the exact
 //     look-back kernel (k_scan.cu), which then also reports the precise violation.  Results are
@@ -179,7 +180,7 @@ __device__ __forceinline__ bool detect_phase(const ByteSrc& B, const uint32_t* f
         uint32_t bits = fastq_eval(B, p0, p1, p2, p3, 0u, 0u, key);
         if (bits & (SBR_ST_INVALID_SEP | SBR_ST_UNEQUAL_LEN)) continue;
         if (p3 + 1 < nbytes && B(p3 + 1) != '@') continue;
-        if (found < 0) found = (int)h;  // ties are settled by k_scan_finish's exact check
+        if (found < 0) found = (int)h;  // ties are settled by the epilogue's exact check (scan_finish)
     }
     if (found < 0) return false;
     h_out = (uint32_t)found;

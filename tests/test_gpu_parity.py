@@ -404,7 +404,7 @@ def test_fasta_empty_sequences_inside_a_large_batch(gpu):
 
 def test_adversarial_phase_detection(gpu):
     """quality strings made of '@' and headers/sequences that mimic other lines: whatever phase a region
-    guesses, the result must be the exact scan's (k_scan_finish verifies, the look-back scan re-runs)"""
+    guesses, the result must be the exact scan's (the scan's epilogue verifies, the look-back scan re-runs)"""
     rng = random.Random(77)
     out = bytearray()
     for i in range(40000):

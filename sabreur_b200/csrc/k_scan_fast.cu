@@ -60,6 +60,11 @@ constexpr int FAST_STAGES = SBR_SCAN_SINGLE ? 1 : 2;
 // still addressable in shared memory at (stage base + position - tile start)
 constexpr int TAIL_PAD = 512;
 __host__ __device__ constexpr int stage_stride(int fmt) { return (fmt == SBR_FMT_FASTQ ? TAIL_PAD : 0) + FAST_TILE; }  // FASTA has no use for the pad
+// Where does the time go?  Experimental builds cut the tile loop short (results are wrong: bench with SBR_DEBUG_ABLATE=1):
+//   1: no record evaluation   2: no compaction either   3: loads, barriers and the next tile's issue only
+#ifndef SBR_ABLATE
+#define SBR_ABLATE 0
+#endif
 #ifndef SBR_WL_CAP
 #define SBR_WL_CAP (SBR_SCAN_SINGLE ? 284 : 188)
 #endif
@@ -419,6 +424,14 @@ __global__ void __maxnreg__(SBR_SCAN_NREG) k_scan_fast(FastArgs A) {
         const uint32_t valid = min((uint32_t)FAST_TILE, A.nbytes - lo);
         const uint8_t* sm = stage_buf + s * STAGE_STRIDE;
         mbar_wait(&S.full_bar[s], parity);
+#if SBR_ABLATE >= 3
+        if (true) {
+            if (tid == 0 && tile + 1 >= t_hi) S.done = 1;  // (before the barrier: every thread must take the same exit)
+            __syncthreads();
+            if (warp == 0 && lane == 0 && tile + 1 < t_hi) issue(0, tile + 1);
+            continue;
+        }
+#endif
 
         // ---- newline masks of this lane's 48 bytes in each unit of the warp's slice ---------------------
         const uint32_t woff = (uint32_t)warp * WARP_SLICE + (uint32_t)lane * SCAN_BYTES_PER_THREAD;
@@ -451,7 +464,7 @@ __global__ void __maxnreg__(SBR_SCAN_NREG) k_scan_fast(FastArgs A) {
 
         // ---- compact the slice's newline positions (ascending) into the warp's list ---------------------
         uint32_t start_bal[FASTA_CHUNKS] = {};  // FASTA: per 32 list entries, which ones are record starts
-        if (fits) {
+        if (fits && SBR_ABLATE < 2) {
             uint32_t unit_base = 0;  // newlines in the slice's earlier units
 #pragma unroll
             for (int j = 0; j < FAST_UNITS; ++j) {
@@ -563,7 +576,7 @@ __global__ void __maxnreg__(SBR_SCAN_NREG) k_scan_fast(FastArgs A) {
 
         if (FMT == SBR_FMT_FASTQ) {
             if (!was_synced) {  // uniform: only the first tile(s) of a region, until eight newlines were seen
-                if (tid == 0 && !S.fail) {  // (a slice over capacity has no list to read from)
+                if (SBR_ABLATE < 2 && tid == 0 && !S.fail) {  // (a slice over capacity has no list to read from)
                     const ByteSrc B{sm, A.text, lo, lo + valid};
                     uint32_t nf = S.nfirst;
                     for (int v = 0; v < FAST_WARPS && nf < 8; ++v) {
@@ -604,7 +617,7 @@ __global__ void __maxnreg__(SBR_SCAN_NREG) k_scan_fast(FastArgs A) {
                 }
                 __syncthreads();
             }
-            if (S.synced && fits && !S.fail) {  // (S.fail: some slice of the CTA may have published nothing usable)
+            if (SBR_ABLATE < 1 && S.synced && fits && !S.fail) {  // (S.fail: some slice of the CTA may have published nothing usable)
                 const uint32_t h = S.h, fo = S.first_owned;
                 const uint32_t L0 = base + pre_n;  // region-local index of the slice's first newline
                 // entries i of this slice that end a record: (h + L0 + i) % 4 == 3.  TWO lanes per record (a 4.5 KB

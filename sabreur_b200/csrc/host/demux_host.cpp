@@ -200,6 +200,7 @@ public:
     Pass(const std::string& path, std::vector<FILE*> bin_files, const std::vector<std::string>& barcodes, uint8_t mismatch,
          Format out_format, int level, const HostOptions& opt, RunStats* stats, const std::atomic<bool>* cancel = nullptr)
         : path_(path), opt_(opt), out_format_(out_format), level_(level), stats_(stats), cancel_(cancel) {
+        const auto t_setup = Clock::now();
         n_bins_ = (uint32_t)barcodes.size() + 1;
         sinks_.resize(n_bins_);
         for (uint32_t b = 0; b < n_bins_; ++b) sinks_[b].fh = bin_files[b];
@@ -240,6 +241,7 @@ public:
                     throw std::runtime_error(std::string("sbr_slot_buffer failed: ") + sbr_last_error(gpus_[g].ctx));
             }
         }
+        if (stats_) stats_->setup_s += secs(t_setup, Clock::now());
     }
     ~Pass() {
         if (!error_ && !gpus_.empty() && gpus_.back().ctx) { give_pooled(pool_key_, gpus_); return; }
@@ -732,6 +734,7 @@ std::pair<Counts&, std::string> pe_demux(const std::string& forward, const std::
         }
         if (stats) {
             stats->read_s += st[mate].read_s; stats->gpu_wait_s += st[mate].gpu_wait_s; stats->write_s += st[mate].write_s;
+            stats->setup_s = std::max(stats->setup_s, st[mate].setup_s);
             stats->total_s = std::max(stats->total_s, st[mate].total_s) + (opt.parallel_mates ? 0.0 : (mate ? st[0].total_s : 0.0));
             stats->bytes_in += st[mate].bytes_in; stats->records += st[mate].records; stats->batches += st[mate].batches;
             stats->respeculated += st[mate].respeculated;

@@ -54,6 +54,7 @@ struct HostOptions {
 
 struct RunStats {  // where the wall time went (reported by the CLI with --timing)
     double read_s = 0, gpu_wait_s = 0, write_s = 0, total_s = 0;
+    double setup_s = 0;  // contexts, pinned slots, device workspaces, the match table (before the first byte is read)
     uint64_t bytes_in = 0, records = 0, batches = 0, respeculated = 0;
 };
 

@@ -301,6 +301,9 @@ int main(int argc, char** argv) {
                             "%llu bytes in, %llu records, %llu batches, %llu re-submitted\n",
                     rs.total_s, rs.read_s, rs.gpu_wait_s, rs.write_s, (unsigned long long)rs.bytes_in, (unsigned long long)rs.records,
                     (unsigned long long)rs.batches, (unsigned long long)rs.respeculated);
+        if (cli.timing)
+            fprintf(stderr, "timing: process %.3f s since main() | GPU setup (contexts, pinned slots, workspaces, match table) %.3f s\n",
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count(), rs.setup_s);
     } catch (const ShortReadPanic& e) {
         fprintf(stderr, "thread 'main' panicked: range end index out of range for slice (%s)\n", e.what());
         return EX_PANIC;

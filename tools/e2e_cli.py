@@ -92,6 +92,8 @@ def main():
             sys.exit(r.stdout + r.stderr)
         m = re.search(r"timing: total ([\d.]+) s \| read\+decompress ([\d.]+) s \| waiting for the GPU ([\d.]+) s \| gather\+compress\+write ([\d.]+) s \| (\d+) bytes in, (\d+) records, (\d+) batches, (\d+) re-submitted", r.stderr)
         total, rd, gw, wr, nbytes, nrec, nb, resub = (float(x) for x in m.groups())
+        m2 = re.search(r"timing: process ([\d.]+) s since main\(\) \| GPU setup [^)]*\) ([\d.]+) s", r.stderr)
+        process_s, setup_s = (float(x) for x in m2.groups()) if m2 else (None, None)
         in_bytes = sum(os.path.getsize(p) for p in paths)
         out_bytes = sum(os.path.getsize(os.path.join(d, "out", f)) for f in os.listdir(os.path.join(d, "out")))
         print(json.dumps({
@@ -100,6 +102,7 @@ def main():
             "wall_s": wall, "reads_per_s": nrec / wall, "input_file_bytes": in_bytes, "text_bytes": int(nbytes), "output_bytes": out_bytes,
             "host_threads": os.cpu_count(), "inflate_threads": a.inflate_threads or "default (min(16, cores))",
             "reader_text_GBps": nbytes / rd / 1e9 if rd > 0 else None,
+            "process_s": process_s, "gpu_setup_s": setup_s,
             "pipeline_s": {"total": total, "reader_decompress": rd, "gpu_thread_waiting": gw, "writer_gather_compress_write": wr},
             "batches": int(nb), "resubmitted": int(resub),
             "note": "reader, GPU thread and writer run concurrently: the stages overlap, the slowest one is the wall"}))

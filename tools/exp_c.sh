@@ -1,3 +1,4 @@
+# round 2, session c: occupancy variants of the scan (build them first: python -m sabreur_b200.build --variant wl160 -DSBR_WL_CAP=160; --variant wl160r40 -DSBR_WL_CAP=160 -DSBR_SCAN_NREG=40; --variant r40 -DSBR_SCAN_NREG=40)
 source tools/gpu_exp.sh c
 L=$PWD/sabreur_b200
 run overlap "" --also none

@@ -1,3 +1,4 @@
+# round 2, session f: staggered CTA starts (the SBR_SCAN_STAGGER_NS knob was removed after this measurement: no effect) + ncu launch list
 source tools/gpu_exp.sh f
 TAG=f
 timeout 300 python -m pytest tests/test_shard_gpu.py -x -q 2>&1 | tail -3

@@ -1,3 +1,4 @@
+# round 2, session g: ncu --set full captures of the big launches (profiles/r2_*_ncu.txt)
 O=gpurun_out; TAG=g
 SMALL="--units-per-gpu 6000000 --steps 1 --warmup 1 --no-e2e --no-cpu --no-verify-merge --also none"
 python bench.py $SMALL > $O/ncu_plain2_$TAG.log 2>&1 &&

@@ -1,3 +1,4 @@
+# round 2, session j: ablation builds of the scan (python -m sabreur_b200.build --variant abl$v -DSBR_ABLATE=$v for v in 1 2 3)
 source tools/gpu_exp.sh j
 L=$PWD/sabreur_b200
 export SBR_DEBUG_ABLATE=1

@@ -126,6 +126,7 @@ struct Cli {
     bool force = false, quiet = false, timing = false, sequential_mates = false;
     int gpus = 1;
     int batch_mb = 256;
+    bool batch_mb_given = false;
 };
 
 long parse_u8(const std::string& name, const char* v) {
@@ -173,7 +174,7 @@ Cli parse_cli(int argc, char** argv) {
         else if (key == "--timing") c.timing = true;
         else if (key == "--sequential-mates") c.sequential_mates = true;
         else if (key == "--gpus") c.gpus = std::max(1, atoi(value(i, key, inl)));
-        else if (key == "--batch-mb") c.batch_mb = std::max(1, atoi(value(i, key, inl)));
+        else if (key == "--batch-mb") { c.batch_mb = std::max(1, atoi(value(i, key, inl))); c.batch_mb_given = true; }
         else if (a.size() > 1 && a[0] == '-') usage_error("unexpected argument '" + a + "' found");
         else pos.push_back(a);
     }
@@ -251,6 +252,22 @@ int main(int argc, char** argv) {
         HostOptions opt;
         opt.n_gpus = cli.gpus;
         opt.batch_bytes = (uint64_t)cli.batch_mb << 20;
+        if (!cli.batch_mb_given) {
+            // small inputs: do not pin and allocate 256 MiB slots for a file that decompresses to a fraction of that (the
+            // allocation is most of a short run's wall time).  The estimate only has to err on the large side.
+            auto estimate = [](const std::string& path, Format f) -> uint64_t {
+                struct stat st;
+                if (stat(path.c_str(), &st) != 0 || !S_ISREG(st.st_mode)) return UINT64_MAX;
+                const uint64_t ratio = f == Format::No ? 1 : (f == Format::Gzip || f == Format::Zstd ? 8 : 12);
+                return (uint64_t)st.st_size * ratio;
+            };
+            uint64_t est = estimate(cli.forward, forward_format);
+            if (is_pe) est = std::max(est, estimate(cli.reverse, which_format(cli.reverse)));
+            if (est != UINT64_MAX) {
+                const uint64_t want = std::max<uint64_t>(32ull << 20, ((est + est / 8) | ((1ull << 20) - 1)) + 1);
+                opt.batch_bytes = std::min(opt.batch_bytes, want);
+            }
+        }
         opt.parallel_mates = !cli.sequential_mates;
         RunStats rs;
         std::string unknown_paths[2];

@@ -318,7 +318,7 @@ private:
                 b.gpu = (int)(seq % G_);
                 b.slot = (uint32_t)((seq / G_) % S_);
                 uint8_t* buf = gpus_[b.gpu].slot_host[b.slot];
-                if (carry.size() > reserve_) throw std::runtime_error("a single record is larger than the batch reserve");
+                if (carry.size() > reserve_) throw std::runtime_error("a single record is larger than the room reserved for it (1/8 of a batch, 16 MiB at most): raise --batch-mb");
                 b.off = reserve_ - carry.size();
                 std::memcpy(buf + b.off, carry.data(), carry.size());
                 // A batch holds at most max_records records (the library's default: batch_bytes / 32 + 16).  A FASTQ

@@ -264,7 +264,7 @@ int main(int argc, char** argv) {
             uint64_t est = estimate(cli.forward, forward_format);
             if (is_pe) est = std::max(est, estimate(cli.reverse, which_format(cli.reverse)));
             if (est != UINT64_MAX) {
-                const uint64_t want = std::max<uint64_t>(32ull << 20, ((est + est / 8) | ((1ull << 20) - 1)) + 1);
+                const uint64_t want = std::max<uint64_t>(64ull << 20, ((est + est / 8) | ((1ull << 20) - 1)) + 1);
                 opt.batch_bytes = std::min(opt.batch_bytes, want);
             }
         }

@@ -270,8 +270,9 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
     c->overlap = (cfg->flags & SBR_CFG_OVERLAP) != 0;
     if (c->overlap) {
         // does one match CTA fit on an SM beside four CTAs of the scan?  (228 KB of shared memory per SM, 1 KB reserved per
-        // CTA.)  If it does not -- a table of more than ~800 bins -- the kernels would take turns instead of sharing
-        // the SMs, which is slower than running them back to back: fall back to one stream.
+        // CTA.)  Tables of more than ~800 bins need the lean kernel for that (16-bit counters, see k_match.cu).  If nothing
+        // fits the kernels would take turns instead of sharing the SMs, which is slower than running them back to back:
+        // fall back to one stream.
         size_t scan_smem = 0;
         for (uint32_t f = SBR_FMT_FASTA; f <= SBR_FMT_FASTQ; ++f)
             if (cfg->fmt == SBR_FMT_AUTO || cfg->fmt == f) scan_smem = std::max(scan_smem, scan_fast_smem_bytes(f));
@@ -280,8 +281,9 @@ static int create_impl(sbr_ctx* c, const sbr_config* cfg) {
         auto fits = [&](bool lean) {
             return 4 * (scan_smem + 1024) + std::max(match_smem(n, k, c->nbins, !c->packed, lean), scatter) + 1024 <= 228 * 1024;
         };
-        // a warp's slice must stay below 65536 records for the 16-bit counters (one CTA per SM, 8 warps each)
-        const bool lean_ok = c->packed && (uint64_t)c->max_records / ((uint64_t)c->sms * 8u) < 60000u;
+        // 16-bit counters and offsets: the records of a whole CTA (8 warp slices, each rounded up to 32; one CTA per SM)
+        // must number fewer than 65536 -- a single bin may hold all of them
+        const bool lean_ok = c->packed && (uint64_t)c->max_records / (uint64_t)c->sms + 256u < 65536u;
         if (getenv("SBR_FORCE_LEAN") && lean_ok) c->lean = true;          // (tests: the lean kernel on small tables)
         else if (!fits(false) && lean_ok && fits(true)) c->lean = true;
         if (!fits(c->lean) && !getenv("SBR_OVERLAP_FORCE")) { c->overlap = false; c->lean = false; }

@@ -106,9 +106,10 @@ __device__ __forceinline__ uint32_t same_bin_lanes(uint32_t bin, uint32_t nbits,
 // FUSED (cooperative launch, every CTA resident): kernel 3 follows in the same launch -- grid barrier, the per-bin
 // scans over CTAs spread over the grid, grid barrier, cursors from the counts still sitting in shared memory, scatter.
 // LEAN (packed modes only): the shared-memory diet for big tables that have to fit beside the record scan (overlapped
-// mode, one CTA per SM next to four of the scan's): per-warp bin counters are 16 bits wide (a warp's slice holds fewer
-// than 65536 records), cursors are kept as {32-bit CTA base per bin} + {16-bit offset per warp and bin}, and the region
-// prefix and the barcode table are read from global memory instead of a shared copy.
+// mode, one CTA per SM next to four of the scan's): per-warp bin counters are 16 bits wide, cursors are kept as
+// {32-bit CTA base per bin} + {16-bit offset per warp and bin} (the context only selects this kernel when a whole CTA's
+// slices hold fewer than 65536 records), and the region prefix and the barcode table are read from global memory instead
+// of a shared copy.
 template <int MODE, bool FUSED, bool LEAN>
 __global__ void __launch_bounds__(MATCH_THREADS) k_match(const MatchArgs A) {
     const RecSource& src = A.src;

@@ -191,6 +191,28 @@ def test_lean_match_kernel_equals_oracle(gpu, name, flags, monkeypatch):
         dm.wait((nb - 1) % 2)
 
 
+@pytest.mark.parametrize("lean", [False, True])
+def test_every_read_in_one_bin(gpu, lean, monkeypatch):
+    """the counters' worst case: all records of every warp slice and every CTA fall into ONE bin (here: unknown, and then
+    the first barcode), with the plain and with the lean (16-bit) match kernel, one CTA per SM"""
+    torch, dmx, ffi = gpu["torch"], gpu["demux"], gpu["ffi"]
+    if lean:
+        monkeypatch.setenv("SBR_FORCE_LEAN", "1")
+    rng = random.Random(8)
+    bcs = [b"ACGTACGTAC"] + [bytes(rng.choices(b"ACGT", k=10)) for _ in range(1500)]
+    n = 400_000
+    for pre, want_bin in ((b"NNNNNNNNNN", len(bcs)), (b"ACGTACGTAC", 0)):
+        text = b"".join(b">r%07d\n" % i + pre + b"ACGTTGCATTGACCA\n" for i in range(n))
+        t = torch.frombuffer(bytearray(text + b"\0" * 64), dtype=torch.uint8).cuda()
+        with dmx.Demux(bcs, 1, fmt=1, batch_bytes=len(text) + 4096, max_records=n + 16, flags=ffi.CFG_OVERLAP) as dm:
+            dm.demux_device(0, t.data_ptr(), len(text), final=True)
+            b = dm.wait(0)
+        assert b.n_records == n and b.status == 0
+        assert int(b.bin_count[want_bin]) == n and int(b.bin_count.sum()) == n
+        assert np.array_equal(b.order, np.arange(n, dtype=np.uint32))
+        assert (b.assign == want_bin).all()
+
+
 def test_scan_stats_count_handed_over_batches(gpu):
     """the device-side counters bench.py reads: a malformed batch is handed to the exact scan and counted"""
     torch, dmx, ffi = gpu["torch"], gpu["demux"], gpu["ffi"]

@@ -202,12 +202,12 @@ def test_every_read_in_one_bin(gpu, lean, monkeypatch):
     bcs = [b"ACGTACGTAC"] + [bytes(rng.choices(b"ACGT", k=10)) for _ in range(1500)]
     n = 400_000
     for pre, want_bin in ((b"NNNNNNNNNN", len(bcs)), (b"ACGTACGTAC", 0)):
-        text = b"".join(b">r%07d\n" % i + pre + b"ACGTTGCATTGACCA\n" for i in range(n))
+        text = b"".join(b">r%07d\n" % i + pre + b"ACGTTGCATTGACCA" * 4 + b"\n" for i in range(n))
         t = torch.frombuffer(bytearray(text + b"\0" * 64), dtype=torch.uint8).cuda()
         with dmx.Demux(bcs, 1, fmt=1, batch_bytes=len(text) + 4096, max_records=n + 16, flags=ffi.CFG_OVERLAP) as dm:
             dm.demux_device(0, t.data_ptr(), len(text), final=True)
             b = dm.wait(0)
-        assert b.n_records == n and b.status == 0
+        assert b.n_records == n and b.status == 0 and b.scan_path == 1
         assert int(b.bin_count[want_bin]) == n and int(b.bin_count.sum()) == n
         assert np.array_equal(b.order, np.arange(n, dtype=np.uint32))
         assert (b.assign == want_bin).all()

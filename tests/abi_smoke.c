@@ -34,6 +34,24 @@ int main(void) {
     printf(" |");
     for (i = 0; i < res.n_records; ++i) printf(" %u", (unsigned)res.assign[i]);
     printf("\n");
+    {   /* the device-resident entry points: the same batch from device memory, match + partition on the slot's own stream */
+        sbr_ctx* ctx2 = NULL;
+        void* d_text = NULL;
+        uint64_t stats[2] = {0, 0};
+        sbr_result res2;
+        cfg.fmt = SBR_FMT_FASTQ;
+        cfg.flags = SBR_CFG_OVERLAP;
+        if (sbr_create(&ctx2, &cfg) != SBR_OK) { fprintf(stderr, "create 2: %s\n", sbr_last_error(NULL)); return 8; }
+        if (sbr_dev_alloc(0, 4096, &d_text) != SBR_OK || sbr_dev_upload(0, d_text, buf, 4096) != SBR_OK) return 9;
+        if (sbr_demux_device(ctx2, 0, (const uint8_t*)d_text, sizeof text - 1, 1, NULL) != SBR_OK) return 10;
+        if (sbr_device_join(ctx2, NULL) != SBR_OK || sbr_scan_stats(ctx2, stats, 0) != SBR_OK) return 11;
+        if (sbr_wait(ctx2, 0, &res2) != SBR_OK || res2.n_records != res.n_records) return 12;
+        for (i = 0; i < res2.n_records; ++i)
+            if (res2.assign[i] != res.assign[i]) return 13;
+        if (stats[0] + stats[1] != 1) return 14;
+        sbr_dev_free(0, d_text);
+        sbr_destroy(ctx2);
+    }
     sbr_destroy(ctx);
     return 0;
 }

@@ -596,7 +596,8 @@ def test_plain_c_caller(gpu):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = os.path.join(root, "sabreur_b200", "bin", "abi_smoke")
     libdir = os.path.join(root, "sabreur_b200", "lib")
-    if not os.path.exists(exe):
+    src = os.path.join(root, "tests", "abi_smoke.c")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
         os.makedirs(os.path.dirname(exe), exist_ok=True)
         subprocess.check_call(["gcc", "-std=c99", "-o", exe, os.path.join(root, "tests", "abi_smoke.c"), "-L" + libdir,
                                "-lsabreur_gpu", "-Wl,-rpath," + libdir])

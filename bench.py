@@ -414,12 +414,18 @@ def run_block(env: Env, name: str, units: int, primary: bool) -> dict:
     w = synth.WORKLOADS[name]
     mates = (0, 1) if w.paired else (0,)
     rec = w.rec_bytes
-    bu = args.batch_units or (3_000_000 if w.fmt == _ffi.FMT_FASTQ else 3_600_000)
+    tab = synth.table(w)
+    bcs = [bytes(r) for r in tab]
+    # Batch size: the scan cuts a batch into one region of whole tiles per resident CTA, so batches of
+    # rows x regions x tile bytes (the largest that stays below the 1 GiB a batch may hold) load every region evenly;
+    # 3,000,000-read batches (round 1) left 76 of 592 regions with a 45th tile while the others were done after 44.
+    with demux.Demux(bcs, w.mismatch, fmt=w.fmt, device=env.local_rank, batch_bytes=1 << 20, n_slots=1) as probe:
+        tile_bytes, regions = probe.scan_geometry(w.fmt)
+    row = tile_bytes * regions
+    bu = args.batch_units or ((1 << 30) // row * row // rec)
     bu = max(16, min(bu, units) // 16 * 16)
     if bu * rec > (1 << 30):
         bu = ((1 << 30) // rec) // 16 * 16
-    tab = synth.table(w)
-    bcs = [bytes(r) for r in tab]
     first = env.rank * units  # this rank's shard of the read index space
     # ---- resident shard -----------------------------------------------------------------------------
     texts = []
@@ -649,6 +655,7 @@ def run_block(env: Env, name: str, units: int, primary: bool) -> dict:
         "warmup": args.warmup, "gpu_launches": int(launches),
         "config": {"workload": w.name, "units_per_gpu": units, "batch_reads": bu, "batches_per_step": len(batches),
                    "record_bytes": rec, "resident_bytes_per_gpu": units * rec * len(mates), "device_slots": S,
+                   "batch_geometry": f"{bu * rec // row} x {regions} regions x {tile_bytes}-byte tiles (+{bu * rec % row} bytes)",
                    "scale": f"{env.world * units} of the configuration's {total} {'pairs' if w.paired else 'reads'} "
                             f"({env.world * units / total:.3g}x) over {env.world} GPU(s); a rate metric",
                    "pipeline": ("scan on the caller's stream; match + partition (one cooperative launch) on the slot's own stream, "

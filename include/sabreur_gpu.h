@@ -146,6 +146,10 @@ int sbr_device_join(sbr_ctx* ctx, void* stream);
  * out[0] = batches it finished, out[1] = batches it handed over to the exact look-back scan (these read
  * "no records" on the device until sbr_wait() has re-run them).  Synchronises the device. */
 int sbr_scan_stats(sbr_ctx* ctx, uint64_t out[2], int reset);
+/* Geometry of the region-parallel scan for `fmt` (SBR_FMT_FASTA / SBR_FMT_FASTQ): a batch is cut into at most *regions
+ * contiguous regions (one per resident CTA) of whole tiles of *tile_bytes.  A caller that is free to choose its batch size
+ * gets evenly loaded regions from batches of (a multiple of) regions * tile_bytes bytes, or a little less. */
+int sbr_scan_geometry(const sbr_ctx* ctx, uint32_t fmt, uint32_t* tile_bytes, uint32_t* regions);
 
 /* The first-match lookup table built from the barcode table (debug / test access).
  * Returns the number of entries (4^bc_len) or 0 when the context does not use a LUT. */

@@ -18,7 +18,7 @@ KEY_SHORT, KEY_NONCANON = 1 << 48, 1 << 49
 # every symbol include/sabreur_gpu.h declares
 EXPORTS = [
     "sbr_abi_version", "sbr_device_count", "sbr_create", "sbr_destroy", "sbr_last_error", "sbr_slot_buffer",
-    "sbr_submit", "sbr_wait", "sbr_demux_device", "sbr_slot_device_result", "sbr_device_join", "sbr_scan_stats", "sbr_lut_entries", "sbr_lut_copy",
+    "sbr_submit", "sbr_wait", "sbr_demux_device", "sbr_slot_device_result", "sbr_device_join", "sbr_scan_stats", "sbr_scan_geometry", "sbr_lut_entries", "sbr_lut_copy",
     "sbr_debug_regions", "sbr_timing_collect", "sbr_synth_table", "sbr_synth_record_bytes", "sbr_synth_host", "sbr_synth_device",
     "sbr_dev_alloc", "sbr_dev_free", "sbr_dev_upload", "sbr_dev_download", "sbr_host_alloc_pinned",
     "sbr_host_free_pinned",
@@ -71,6 +71,7 @@ def load():
         "sbr_slot_device_result": (i32, [vp, u32, C.POINTER(SbrResult)]),
         "sbr_device_join": (i32, [vp, vp]),
         "sbr_scan_stats": (i32, [vp, C.POINTER(u64 * 2), i32]),
+        "sbr_scan_geometry": (i32, [vp, u32, C.POINTER(u32), C.POINTER(u32)]),
         "sbr_lut_entries": (u64, [vp]),
         "sbr_lut_copy": (i32, [vp, vp, u64]),
         "sbr_debug_regions": (i32, [vp, u32, vp, u32]),

@@ -22,6 +22,7 @@ uint32_t scan_tiles(uint32_t nbytes);
 // k_scan_fast.cu (region-parallel scan)
 cudaError_t scan_fast_prepare(int device, int* grid_fastq, int* grid_fasta);
 size_t scan_fast_smem_bytes(uint32_t fmt);
+uint32_t scan_fast_tile_bytes();
 uint32_t scan_fast_regions(uint32_t nbytes, int max_regions, uint32_t* tiles_per_region, uint32_t* extra_regions);
 cudaError_t scan_fast_launch(uint32_t fmt, const uint8_t* d_text, uint32_t nbytes, uint32_t max_records, uint32_t cap_r,
                              uint32_t n_regions, uint32_t tiles_per_region, uint32_t extra_regions, uint32_t bc_len,
@@ -625,6 +626,13 @@ extern "C" int sbr_scan_stats(sbr_ctx* c, uint64_t out[2], int reset) {
     out[0] = h[0];
     out[1] = h[1];
     if (reset) CU(c, cudaMemset(c->d_stats, 0, sizeof h));
+    return SBR_OK;
+}
+
+extern "C" int sbr_scan_geometry(const sbr_ctx* c, uint32_t fmt, uint32_t* tile_bytes, uint32_t* regions) {
+    if (!c || (fmt != SBR_FMT_FASTA && fmt != SBR_FMT_FASTQ)) return SBR_E_INVALID_ARG;
+    if (tile_bytes) *tile_bytes = scan_fast_tile_bytes();
+    if (regions) *regions = (uint32_t)(fmt == SBR_FMT_FASTA ? c->fast_grid_a : c->fast_grid_q);
     return SBR_OK;
 }
 

@@ -792,6 +792,8 @@ __global__ void __maxnreg__(SBR_SCAN_NREG) k_scan_fast(FastArgs A) {
 
 }  // namespace
 
+uint32_t scan_fast_tile_bytes() { return (uint32_t)FAST_TILE; }
+
 size_t scan_fast_smem_bytes(uint32_t fmt) {
     return (size_t)FAST_STAGES * stage_stride((int)fmt) +
            (fmt == SBR_FMT_FASTA ? sizeof(FastSmem<SBR_FMT_FASTA>) : sizeof(FastSmem<SBR_FMT_FASTQ>));

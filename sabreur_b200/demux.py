@@ -152,6 +152,13 @@ class Demux:
         self._check(self.lib.sbr_scan_stats(self.h, C.byref(out), int(reset)), "sbr_scan_stats")
         return int(out[0]), int(out[1])
 
+    def scan_geometry(self, fmt: int) -> tuple[int, int]:
+        """(tile bytes, regions) of the region-parallel scan: batches of about regions * tile_bytes * k bytes load every
+        region evenly"""
+        t, r = C.c_uint32(), C.c_uint32()
+        self._check(self.lib.sbr_scan_geometry(self.h, fmt, C.byref(t), C.byref(r)), "sbr_scan_geometry")
+        return int(t.value), int(r.value)
+
     def lut(self) -> np.ndarray | None:
         n = self.lib.sbr_lut_entries(self.h)
         if n == 0:

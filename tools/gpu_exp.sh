@@ -2,7 +2,7 @@
 # quick A/B runs of bench.py variants (HBM-resident loop only): bash tools/gpu_exp.sh TAG
 TAG=${1:-x}
 O=gpurun_out; mkdir -p $O
-Q="--units-per-gpu 30000000 --steps 10 --warmup 3 --no-e2e --no-cpu"
+Q=${Q:-"--units-per-gpu 30000000 --steps 10 --warmup 3 --no-e2e --no-cpu"}
 run() {  # label, env assignments (may be empty), bench args
   local label=$1; shift; local envs=$1; shift
   env $envs timeout 300 python bench.py $Q "$@" > $O/exp_${TAG}_$label.json 2> $O/exp_${TAG}_$label.err || { echo "$label FAILED"; tail -3 $O/exp_${TAG}_$label.err; }

@@ -121,17 +121,57 @@ def merge_counts(local_counts: np.ndarray, group=None) -> np.ndarray:
     return t.cpu().numpy().astype(np.uint64)
 
 
+def _pack(results: list[BatchResult]) -> np.ndarray:
+    """one flat int64 vector for a rank's batch results: [count] + per result [seq, n_records, status, first_bad_record,
+    n_bins] + bin_count + bin_start + order"""
+    parts = [np.array([len(results)], dtype=np.int64)]
+    for r in results:
+        parts.append(np.array([r.seq, r.n_records, r.status, r.first_bad_record, len(r.bin_count)], dtype=np.int64))
+        parts.append(np.asarray(r.bin_count, dtype=np.int64))
+        parts.append(np.asarray(r.bin_start, dtype=np.int64))
+        parts.append(np.asarray(r.order[: r.n_records], dtype=np.int64))
+    return np.concatenate(parts)
+
+
+def _unpack(flat: np.ndarray) -> list[BatchResult]:
+    out, at = [], 1
+    for _ in range(int(flat[0])):
+        seq, n, status, bad, nb = (int(x) for x in flat[at: at + 5])
+        at += 5
+        bin_count = flat[at: at + nb].astype(np.uint32)
+        at += nb
+        bin_start = flat[at: at + nb + 1].astype(np.uint32)
+        at += nb + 1
+        order = flat[at: at + n].astype(np.uint32)
+        at += n
+        out.append(BatchResult(seq, n, bin_count, bin_start, order, status, bad))
+    return out
+
+
 def gather_results(local: list[BatchResult], dst: int = 0, group=None) -> list[BatchResult] | None:
-    """bring every rank's batch results to `dst` (index lists go to the rank that owns the writers)"""
+    """bring every rank's batch results to `dst` (index lists go to the rank that owns the writers).  Plain tensors on the
+    launcher's process group -- sizes first, then the padded payloads -- so that it runs on nccl and gloo alike and nothing
+    is pickled"""
+    import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return list(local)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    out = [None] * world if rank == dst else None
-    dist.gather_object(local, out, dst=dst, group=group)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    flat = _pack(local)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([flat.size], dtype=torch.int64, device=dev), group=group)
+    longest = max(int(x.item()) for x in sizes)
+    mine = torch.zeros(longest, dtype=torch.int64, device=dev)
+    mine[: flat.size] = torch.from_numpy(flat).to(dev)
+    everyone = [torch.empty(longest, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(everyone, mine, group=group)
     if rank != dst:
         return None
-    return [r for part in out for r in part]
+    out = []
+    for size, t in zip(sizes, everyone):
+        out += _unpack(t[: int(size.item())].cpu().numpy())
+    return out
 
 
 def run_sharded(batches: list, world: int, rank: int, run_batch: Callable[[int, object], BatchResult]) -> list[BatchResult]:

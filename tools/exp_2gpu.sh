@@ -1,5 +1,7 @@
+# round 2: two GPUs -- host and merge tests, smoke(), the torchrun bench (both arms)
 O=gpurun_out; mkdir -p $O
 nvidia-smi --query-gpu=index,name --format=csv,noheader
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 900 python -m pytest tests/test_host_gpu.py tests/test_shard_gpu.py -x -q > $O/pytest_2gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_2gpu.log
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 > $O/bench_2gpu.json 2> $O/bench_2gpu.err; echo "bench rc=$?"; tail -2 $O/bench_2gpu.err
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --impl reference --steps 2 --warmup 1 > $O/bench_ref_2gpu.json 2> $O/bench_ref_2gpu.err; echo "ref rc=$?"

@@ -554,11 +554,14 @@ private:
                     bad_flags_ = r.first_bad_flags;
                     bad_record_ = records_before_ + r.first_bad_record;
                 }
-                parallel_for(n_bins_, nthreads, [&](uint32_t bin) { gather_bin(b, bin, nok); });
-                if (out_format_ == Format::No) {
-                    for (auto& s : sinks_)
-                        if (!s.raw.empty() && fwrite(s.raw.data(), 1, s.raw.size(), s.fh) != s.raw.size()) throw std::runtime_error("write failed");
-                } else {
+                // uncompressed output: every bin is its own file, so the thread that gathered a bin also appends it
+                parallel_for(n_bins_, nthreads, [&](uint32_t bin) {
+                    gather_bin(b, bin, nok);
+                    Sink& s = sinks_[bin];
+                    if (out_format_ == Format::No && !s.raw.empty() && fwrite(s.raw.data(), 1, s.raw.size(), s.fh) != s.raw.size())
+                        throw std::runtime_error("write failed");
+                });
+                if (out_format_ != Format::No) {
                     std::vector<Piece> pieces;  // in (bin, offset) order: members of a file are appended in this order
                     for (uint32_t bin = 0; bin < n_bins_; ++bin)
                         for (size_t lo = 0; lo < sinks_[bin].raw.size(); lo += MEMBER)

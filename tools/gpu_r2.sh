@@ -29,15 +29,20 @@ for f in ("$O/bench_$TAG.json", "$O/bench_${TAG}_serial.json"):
               "e2e %.3f G/s" % (b["e2e"]["value"] / 1e9) if b.get("e2e") else "", "self", b["self_check"]["spec_fail"], b["self_check"]["scan_finished"])
 PY
 if [[ " $* " != *" noncu "* ]]; then
-  SMALL="--units-per-gpu 6000000 --steps 1 --warmup 1 --no-e2e --no-cpu"
+  # (each capture only after the same command line has just exited 0 without ncu; under ncu kernels are serialised, so the
+  # launch list shows every kernel's own time, not the overlap)
+  SMALL="--units-per-gpu 7000000 --steps 1 --warmup 1 --no-e2e --no-cpu"
   python bench.py $SMALL > $O/ncu_plain_$TAG.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv python bench.py $SMALL > $O/ncu_launch_$TAG.log 2>&1; echo "ncu launches rc=$?"
-  python bench.py $SMALL --also none > $O/ncu_plain2_$TAG.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:k_scan_fast -s 3 -c 1 -o $O/prof_scan_$TAG -f python bench.py $SMALL --also none > $O/ncu_scan_$TAG.log 2>&1; echo "ncu scan rc=$?"
-  python bench.py $SMALL --also none > $O/ncu_plain3_$TAG.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:k_match -s 3 -c 1 -o $O/prof_match_$TAG -f python bench.py $SMALL --also none > $O/ncu_match_$TAG.log 2>&1; echo "ncu match rc=$?"
-  python bench.py $SMALL --workload cfg5 --also none > $O/ncu_plain4_$TAG.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:'k_scan_fast|k_match' -s 6 -c 2 -o $O/prof_cfg5_$TAG -f python bench.py $SMALL --workload cfg5 --also none > $O/ncu_cfg5_$TAG.log 2>&1; echo "ncu cfg5 rc=$?"
+  ONE="$SMALL --no-verify-merge --also none"
+  python bench.py $ONE > $O/ncu_plain2_$TAG.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:k_scan_fast -s 1 -c 1 -o $O/prof_scan_$TAG -f python bench.py $ONE > $O/ncu_scan_$TAG.log 2>&1; echo "ncu scan rc=$?"
+  python bench.py $ONE > $O/ncu_plain3_$TAG.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:k_match -s 1 -c 1 -o $O/prof_match_$TAG -f python bench.py $ONE > $O/ncu_match_$TAG.log 2>&1; echo "ncu match rc=$?"
+  python bench.py $ONE --workload cfg5 --units-per-gpu 9000000 > $O/ncu_plain4_$TAG.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:'k_scan_fast|k_match' -s 0 -c 2 -o $O/prof_cfg5_$TAG -f python bench.py $ONE --workload cfg5 --units-per-gpu 9000000 > $O/ncu_cfg5_$TAG.log 2>&1; echo "ncu cfg5 rc=$?"
+  python bench.py $ONE --workload cfg4 > $O/ncu_plain5_$TAG.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:'k_scan_fast|k_match' -s 0 -c 2 -o $O/prof_cfg4_$TAG -f python bench.py $ONE --workload cfg4 > $O/ncu_cfg4_$TAG.log 2>&1; echo "ncu cfg4 rc=$?"
 fi
 if [[ " $* " != *" nocli "* ]]; then
   : > $O/e2e_cli_$TAG.jsonl

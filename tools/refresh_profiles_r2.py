@@ -30,7 +30,7 @@ if os.path.exists(os.path.join(G, f"launches_{ltag}.csv")):
     open(os.path.join(P, "r2_launches.csv"), "w").write(open(os.path.join(G, f"launches_{ltag}.csv")).read())
 
 traffic = json.load(open(os.path.join(P, "traffic.json")))
-units = {"cfg3": 3_000_000, "cfg4": 3_000_000, "cfg5": 2_400_000}  # cfg5: the capture (-s 2) is the shard's second, shorter batch
+units = {"cfg3": 3_331_296, "cfg4": 3_331_296, "cfg5": 4_020_112}  # one full batch of 49 tile rows each (the first batch of a shard)
 for rep, out, wl in ((f"prof_scan_{ntag}", "r2_scan_fast_ncu.txt", "cfg3"), (f"prof_match_{ntag}", "r2_match_partition_ncu.txt", None),
                      (f"prof_cfg4_{ntag}", "r2_cfg4_scan_match_ncu.txt", "cfg4"), (f"prof_cfg5_{ntag}", "r2_cfg5_scan_match_ncu.txt", "cfg5")):
     path = os.path.join(G, rep + ".ncu-rep")
@@ -54,8 +54,8 @@ for rep, out, wl in ((f"prof_scan_{ntag}", "r2_scan_fast_ncu.txt", "cfg3"), (f"p
         traffic[wl] = {"k_scan_dram_bytes_per_launch": int(rd + wr), "read": int(rd), "write": int(wr), "reads_per_launch": units[wl],
                        "source": f"profiles/{out}"}
 traffic["_how"] = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE k_scan_fast launch per workload (ncu --set full --clock-control none, "
-                   f"round 2 gpurun session {ntag}, bench.py --units-per-gpu 6000000 --no-verify-merge: cfg3 / cfg4: one full batch of 3,000,000 FASTQ reads "
-                   "(963 MB of text); cfg5: the 2,400,000-read batch (638 MB) that ends the 6 M-read shard). Algorithmic bytes of the cfg3 launch: 3e6 x (321 + 8) = 987,000,000; the "
+                   f"round 2 gpurun session {ntag}, bench.py --units-per-gpu 7000000 (cfg5: 9000000) --no-verify-merge: the shard's first batch, 49 tile rows = "
+                   "3,331,296 FASTQ reads or 4,020,112 FASTA reads (1.069 GB of text). Algorithmic bytes of the cfg3 launch: 3,331,296 x (321 + 8) = 1,095,996,384; the "
                    "excess are the tiles every region runs over into (and prefetches) to finish its last record.")
 json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 d = json.loads(open(os.path.join(P, "r2_bench.json")).read())

@@ -633,11 +633,11 @@ def run_block(env: Env, name: str, units: int, primary: bool) -> dict:
 
     # ---- CPU baseline beside it (rank 0, N = 1, primary workload only) -------------------------------------
     cpu = None
-    if primary and env.rank == 0 and env.world == 1 and not args.no_cpu:
-        probe_n = 200_000
+    if env.rank == 0 and env.world == 1 and not args.no_cpu:  # (a quarter of the sample for the secondary workloads)
+        probe_n = 200_000 if primary else 50_000
         probe = texts[0][: probe_n * rec].cpu().numpy()
         s1, _, _ = cpu_reference(w, tab, probe, rec, 1)
-        n = int(max(probe_n, min(units, 16_000_000, s1 * args.cpu_seconds)))
+        n = int(max(probe_n, min(units, 16_000_000, s1 * args.cpu_seconds * (1.0 if primary else 0.25))))
         sample = texts[0][: n * rec].cpu().numpy()
         threads = os.cpu_count() or 1
         single, dt1, allc = cpu_reference(w, tab, sample, rec, threads)
@@ -655,7 +655,8 @@ def run_block(env: Env, name: str, units: int, primary: bool) -> dict:
         "warmup": args.warmup, "gpu_launches": int(launches),
         "config": {"workload": w.name, "units_per_gpu": units, "batch_reads": bu, "batches_per_step": len(batches),
                    "record_bytes": rec, "resident_bytes_per_gpu": units * rec * len(mates), "device_slots": S,
-                   "batch_geometry": f"{bu * rec // row} x {regions} regions x {tile_bytes}-byte tiles (+{bu * rec % row} bytes)",
+                   "batch_geometry": f"{-(-bu * rec // row)} tile rows x {regions} regions x {tile_bytes}-byte tiles "
+                                     f"({-(-bu * rec // row) * row - bu * rec} bytes short of full rows)",
                    "scale": f"{env.world * units} of the configuration's {total} {'pairs' if w.paired else 'reads'} "
                             f"({env.world * units / total:.3g}x) over {env.world} GPU(s); a rate metric",
                    "pipeline": ("scan on the caller's stream; match + partition (one cooperative launch) on the slot's own stream, "
@@ -719,7 +720,7 @@ def main():
             "cpu_baseline": main_block["cpu_baseline"], "e2e": main_block["e2e"], "clocks": main_block["clocks"],
             "gpu_launches": main_block["gpu_launches"] + sum(b["gpu_launches"] for b in blocks.values()),
             "verify_merge": merged,
-            "workloads": {k: {kk: vv for kk, vv in b.items() if kk != "cpu_baseline"} for k, b in blocks.items()},
+            "workloads": blocks,
         }
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)

@@ -65,6 +65,10 @@ __host__ __device__ constexpr int stage_stride(int fmt) { return (fmt == SBR_FMT
 #ifndef SBR_ABLATE
 #define SBR_ABLATE 0
 #endif
+#ifndef SBR_PF_AHEAD
+#define SBR_PF_AHEAD 1  // L2 prefetch distance in tiles.  Measured (profiles/r2_experiments.md): 2, 3, 4 are slower, 204 -> 214 / 231 / 264 us
+#endif
+constexpr int PF_AHEAD = SBR_PF_AHEAD;
 #ifndef SBR_WL_CAP
 #define SBR_WL_CAP (SBR_SCAN_SINGLE ? 284 : 188)
 #endif
@@ -364,11 +368,19 @@ __global__ void __maxnreg__(SBR_SCAN_NREG) k_scan_fast(FastArgs A) {
         uint32_t bytes = (valid + 15u) & ~15u;  // the text buffer is padded to 16 bytes
         mbar_expect_tx(&S.full_bar[s], bytes);
         bulk_g2s_hint(stage_buf + s * STAGE_STRIDE, A.text + lo, bytes, &S.full_bar[s], text_policy);
-        if (FAST_STAGES == 1 && tile + 1 < A.ntiles) {
+        if (FAST_STAGES == 1) {
             // single-buffered: the load of the NEXT tile can only start when this one has been scanned, so at least
-            // bring it into L2 now (the region's last tile prefetches the one a FASTQ region runs over into)
-            const uint32_t nlo = lo + (uint32_t)FAST_TILE;
-            bulk_prefetch_l2(A.text + nlo, (min((uint32_t)FAST_TILE, A.nbytes - nlo) + 15u) & ~15u, text_policy);
+            // bring the tile(s) behind it into L2 now.  (ncu: half of the text's sectors meet their own prefetch still in
+            // flight when the load is issued one tile period later -- yet prefetching further ahead is slower: the tiles
+            // needed next then queue behind less urgent ones.)  Nothing is prefetched past the tile a region runs over
+            // into (t_hi).
+            const uint32_t first = tile == t_lo ? 1u : (uint32_t)PF_AHEAD;  // a region's first load brings in all of them
+            for (uint32_t k = first; k <= (uint32_t)PF_AHEAD; ++k) {
+                const uint32_t nt = tile + k;
+                if (nt > t_hi || nt >= A.ntiles) break;
+                const uint32_t nlo = nt * (uint32_t)FAST_TILE;
+                bulk_prefetch_l2(A.text + nlo, (min((uint32_t)FAST_TILE, A.nbytes - nlo) + 15u) & ~15u, text_policy);
+            }
         }
     };
 

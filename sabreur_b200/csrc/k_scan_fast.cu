@@ -66,7 +66,7 @@ __host__ __device__ constexpr int stage_stride(int fmt) { return (fmt == SBR_FMT
 #define SBR_ABLATE 0
 #endif
 #ifndef SBR_PF_AHEAD
-#define SBR_PF_AHEAD 1  // L2 prefetch distance in tiles.  Measured (profiles/r2_experiments.md): 2, 3, 4 are slower, 204 -> 214 / 231 / 264 us
+#define SBR_PF_AHEAD 1  // L2 prefetch distance in tiles (0 = none).  Measured (profiles/r2_experiments.md): none 215 us, 1: 204, 2 / 3 / 4: 214 / 231 / 264
 #endif
 constexpr int PF_AHEAD = SBR_PF_AHEAD;
 #ifndef SBR_WL_CAP
@@ -375,6 +375,7 @@ __global__ void __maxnreg__(SBR_SCAN_NREG) k_scan_fast(FastArgs A) {
             // needed next then queue behind less urgent ones.)  Nothing is prefetched past the tile a region runs over
             // into (t_hi).
             const uint32_t first = tile == t_lo ? 1u : (uint32_t)PF_AHEAD;  // a region's first load brings in all of them
+            if (PF_AHEAD == 0) return;
             for (uint32_t k = first; k <= (uint32_t)PF_AHEAD; ++k) {
                 const uint32_t nt = tile + k;
                 if (nt > t_hi || nt >= A.ntiles) break;

@@ -200,7 +200,7 @@ private:
             if (ix[0] != 0 || le32(ix + index_size - 4) != crc_of(ix, index_size - 4)) return false;
             size_t at = 1;
             uint64_t nrec;
-            if (!get_vli(ix, index_size - 4, at, nrec) || nrec > (1ull << 32)) return false;
+            if (!get_vli(ix, index_size - 4, at, nrec) || nrec > index_size / 2) return false;  // (a record takes >= 2 bytes)
             std::vector<Unit> blocks((size_t)nrec);
             uint64_t blocks_bytes = 0;
             for (auto& b : blocks) {

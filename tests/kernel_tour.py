@@ -3,10 +3,10 @@
 pipeline (plain and lean match kernel), streamed batches through the region-parallel and the look-back scan, a batch that
 is handed over, FASTA and FASTQ.  Everything is checked against the oracle, so the plain run is a test of its own.
 
-    python tools/sanitize_smoke.py && compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
+    python tests/kernel_tour.py && compute-sanitizer --tool memcheck python tests/kernel_tour.py
 
 (Round 2: compute-sanitizer is closed on this GPU pool -- "runs under it have left GPUs needing a reset" -- so only the
-plain run exists; tests/test_gpu_tour.py keeps it in the GPU suite.)"""
+plain run exists; tests/test_gpu_tour.py keeps it in the GPU suite.  Test infrastructure: the oracle is the checker.)"""
 import os
 import sys
 
@@ -77,7 +77,7 @@ def main():
     for text in (fq, fa, short):
         for flags in (0, _ffi.CFG_EXACT_SCAN, _ffi.CFG_GENERIC, _ffi.CFG_NO_FUSE):
             streamed(text, bcs, 1, flags)
-    print("sanitize_smoke: all ok")
+    print("kernel_tour: all ok")
 
 
 if __name__ == "__main__":

@@ -98,6 +98,34 @@ def test_synthetic_slice_parity(gpu, name, n, flags):
         assert all(got["scan_paths"]), "clean synthetic batches must finish in the region-parallel scan"
 
 
+def _synth_goldens():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "synth_goldens.json")))
+
+
+@pytest.mark.parametrize("g", _synth_goldens(), ids=lambda g: f"{g['workload']}-mate{g['mate']}")
+def test_gpu_reproduces_the_committed_synthetic_goldens(gpu, g):
+    """the CUDA path against digests COMMITTED in tests/golden/synth_goldens.json (made from the oracle by
+    make_synth_goldens.py): device generator, scan, match and partition, without the oracle in the loop"""
+    torch, synth, dmx, ffi = gpu["torch"], gpu["synth"], gpu["demux"], gpu["ffi"]
+    w = synth.WORKLOADS[g["workload"]]
+    tab = synth.table(w)
+    assert hashlib.sha256(tab.tobytes()).hexdigest() == g["table_sha256"]
+    n, rec = g["n"], w.rec_bytes
+    dev = torch.empty(n * rec + 64, dtype=torch.uint8, device="cuda")
+    synth.reads_device(w, tab, g["first"], n, dev.data_ptr(), mate=g["mate"])
+    assert hashlib.sha256(dev[: n * rec].cpu().numpy().tobytes()).hexdigest() == g["text_sha256"]
+    for flags in (0, ffi.CFG_OVERLAP, ffi.CFG_NO_FUSE | ffi.CFG_NO_LUT):
+        with dmx.Demux([bytes(r) for r in tab], g["mismatch"], fmt=w.fmt, batch_bytes=n * rec + 4096, flags=flags) as dm:
+            dm.demux_device(0, dev.data_ptr(), n * rec, final=True)
+            b = dm.wait(0)
+        assert b.n_records == n and b.status == 0
+        assert hashlib.sha256(b.assign.astype("<u2").tobytes()).hexdigest() == g["assign_sha256"]
+        assert hashlib.sha256(b.order.astype("<u4").tobytes()).hexdigest() == g["order_sha256"]
+        assert int(b.bin_count[-1]) == g["unknown"] and [int(x) for x in b.bin_count[:8]] == g["bin_count_head"]
+
+
 def test_device_resident_batch_equals_oracle(gpu):
     """sbr_demux_device on HBM-resident text (the benchmark path)"""
     torch, synth, dmx = gpu["torch"], gpu["synth"], gpu["demux"]

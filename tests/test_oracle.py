@@ -222,3 +222,27 @@ def test_synth_ref_equals_product_generator(name):
             got = orc.synth_reads(w.fmt, w.read_len, mate, seed, ref_tab, first, n, threads=3 if first == 0 else 1)
             assert got.size == n * w.rec_bytes
             assert np.array_equal(got, want)
+
+
+# --- committed digests of the synthetic workloads (tests/golden/synth_goldens.json, made by make_synth_goldens.py) -------
+def _synth_goldens():
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    return json.load(open(os.path.join(here, "golden", "synth_goldens.json")))
+
+
+@pytest.mark.parametrize("g", _synth_goldens(), ids=lambda g: f"{g['workload']}-mate{g['mate']}")
+def test_oracle_reproduces_the_committed_synthetic_goldens(g):
+    """the oracle today against the digests committed when the workloads were defined: generator, parser, first-match
+    rule and partition cannot drift (together with the GPU path, which is compared with the same file) unnoticed"""
+    from sabreur_b200 import synth
+    w = synth.WORKLOADS[g["workload"]]
+    tab = orc.synth_table(w.cfg_id, w.n_barcodes, w.bc_len, w.min_dist)
+    text = orc.synth_reads(w.fmt, w.read_len, g["mate"], synth.SEED_READS + w.cfg_id, tab, g["first"], g["n"])
+    assert hashlib.sha256(text.tobytes()).hexdigest() == g["text_sha256"]
+    assert hashlib.sha256(tab.tobytes()).hexdigest() == g["table_sha256"]
+    exp = orc.demux(text, [bytes(r) for r in tab], g["mismatch"])
+    assert hashlib.sha256(exp["assign"].astype("<u2").tobytes()).hexdigest() == g["assign_sha256"]
+    assert hashlib.sha256(exp["order"].astype("<u4").tobytes()).hexdigest() == g["order_sha256"]
+    assert int(exp["bin_count"][-1]) == g["unknown"] and [int(x) for x in exp["bin_count"][:8]] == g["bin_count_head"]
